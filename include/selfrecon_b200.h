@@ -1,0 +1,253 @@
+/*
+ * selfrecon_b200.h -- C ABI of libselfrecon_b200.so (B200 / sm_100a).
+ *
+ * This is the drop-in boundary for the SelfRecon per-frame optimisation hot path
+ * (SURVEY.md section 8).  Every entry point takes plain device pointers, sizes and a
+ * cudaStream_t; none allocates, none synchronises the host, none touches torch types.
+ * Each returns SR_OK (0), a negative SR_E* validation code, or a positive cudaError_t
+ * raised by the launch.  The torch-facing shims (selfreconcode_b200/dropin/ *.py) own
+ * allocation and turn non-zero codes into RuntimeError, mirroring the reference's pybind
+ * modules FastMinv, MCGpu, GridSamplerMine, interp2x_boundary3d.
+ *
+ * Reference interface replaced by each group is cited as  <file>:<line>  relative to
+ * jby1993/SelfReconCode.
+ */
+#ifndef SELFRECON_B200_H_
+#define SELFRECON_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __DRIVER_TYPES_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+enum {
+  SR_OK = 0,
+  SR_EINVAL = -1,     /* bad size / null pointer */
+  SR_EUNSUPPORTED = -2, /* shape outside what the kernels are built for */
+  SR_ECAPACITY = -3   /* caller-provided output buffer too small */
+};
+
+/* Library / build identification (used by the "loads and exports" CPU test). */
+int sr_abi_version(void);
+const char* sr_build_info(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched 3x3 inverse + analytic backward.
+ * Replaces FastMinv.Fast3x3Minv / Fast3x3Minv_backward
+ *   (FastMinv/M3x3Inv.cpp:12-59, FastMinv/Matrix3x3InvKernels.cu:22-104).
+ *   ms/invs/grads/outs: [n,3,3] contiguous; checks: [n] bytes (0/1, torch.bool layout).
+ *   |det| < 1e-4  ->  inverse = 0, check = 0 (same threshold, compared in double as the
+ *   reference's `fabs(det)<0.0001` does).
+ * ------------------------------------------------------------------------------------------ */
+int sr_minv3x3_f32(const float* ms, float* invs, uint8_t* checks, int64_t n, cudaStream_t s);
+int sr_minv3x3_f64(const double* ms, double* invs, uint8_t* checks, int64_t n, cudaStream_t s);
+int sr_minv3x3_bwd_f32(const float* grads, const float* invs, float* outs, int64_t n,
+                       cudaStream_t s);
+int sr_minv3x3_bwd_f64(const double* grads, const double* invs, double* outs, int64_t n,
+                       cudaStream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * Marching cubes over a dense SDF grid, shared-vertex indexing, deterministic order.
+ * Replaces MCGpu.mc_gpu (MCGpu/MCGpu.cpp:20-56, MCGpu/CudaKernels.cu:304-521,620-640).
+ *   sdf: [nx,ny,nz] contiguous f32, index (i*ny + j)*nz + k; inside = sdf < iso.
+ * Two calls (the reference also has one blocking readback of its two counters,
+ * CudaKernels.cu:628):
+ *   sr_mc_count : classify pass.  Fills `work` (sr_mc_work_bytes(nx,ny,nz) bytes, caller
+ *                 allocated, kept until sr_mc_emit) and writes counts[0]=#vertices,
+ *                 counts[1]=#faces on the device.
+ *   sr_mc_emit  : writes vertices[V,3] (world: fmaf(v,step,min) per axis) and faces[F,3]
+ *                 int64 (winding reversed like d_conver_ijkd_to_pindex) in CANONICAL order:
+ *                 vertices sorted by owning edge key (i,j,k,dir), faces by (voxel, tri#).
+ *                 Corners that reference a never-created boundary-layer vertex get -1,
+ *                 as in the reference.
+ * ------------------------------------------------------------------------------------------ */
+int64_t sr_mc_work_bytes(int nx, int ny, int nz);
+int sr_mc_count(const float* sdf, int nx, int ny, int nz, float iso, void* work, int32_t* counts,
+                cudaStream_t s);
+int sr_mc_emit(const float* sdf, int nx, int ny, int nz, float iso, float xstep, float ystep,
+               float zstep, float xmin, float ymin, float zmin, const void* work,
+               float* vertices, int64_t vcap, int64_t* faces, int64_t fcap, cudaStream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * 2x-1 trilinear upsample + boundary flag.
+ * Replaces interp2x_boundary3d.forward/backward
+ *   (MCAcc/cuda/interp2x_boundary3d.cpp:17-36, interp2x_boundary3d_kernel.cu:10-239).
+ *   in: [bc,d,h,w] -> out: [bc,2d-1,2h-1,2w-1]; is_boundary: bytes, same shape as out.
+ * ------------------------------------------------------------------------------------------ */
+int sr_interp2x3d_fwd_f32(const float* in, float* out, uint8_t* is_boundary, int bc, int d, int h,
+                          int w, float balance, cudaStream_t s);
+int sr_interp2x3d_bwd_f32(const float* grad_out, float* grad_in, int bc, int d, int h, int w,
+                          cudaStream_t s);
+/* 2-D analogue (MCAcc/cuda/interp2x_boundary2d.cpp:17-36); unused by the reference's Python. */
+int sr_interp2x2d_fwd_f32(const float* in, float* out, uint8_t* is_boundary, int bc, int h, int w,
+                          float balance, cudaStream_t s);
+int sr_interp2x2d_bwd_f32(const float* grad_out, float* grad_in, int bc, int h, int w,
+                          cudaStream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * Trilinear grid sampler, border padding, align_corners=False, with first and second
+ * order backward.  Replaces GridSamplerMine.forward/backward/dbackward
+ *   (MCAcc/cuda/GridSamplerMine.cpp:73-96, GridSamplerMineKernel.cu:160-914).
+ *   input  : [N,C,D,H,W] with element strides istr[5]   (any strides)
+ *   grid   : [N,P,3] contiguous (P = Do*Ho*Wo flattened)
+ *   output / grad_output : [N,C,P] contiguous
+ *   grad_input  : [N,C,D,H,W] contiguous, MUST be zero-filled by the caller (atomics)
+ *   corner_idx (optional, may be NULL): [N,P,3] int32 = floor of the clipped
+ *                 un-normalised coordinate (ix,iy,iz) -- the "skinning indices".
+ * ------------------------------------------------------------------------------------------ */
+int sr_grid_sample3d_fwd_f32(const float* input, const int64_t* istr, const float* grid,
+                             float* output, int32_t* corner_idx, int N, int C, int D, int H, int W,
+                             int64_t P, cudaStream_t s);
+int sr_grid_sample3d_bwd_f32(const float* input, const int64_t* istr, const float* grid,
+                             const float* grad_output, float* grad_input, float* grad_grid, int N,
+                             int C, int D, int H, int W, int64_t P, cudaStream_t s);
+int sr_grid_sample3d_dbwd_f32(const float* gg_input /*[N,C,D,H,W] contiguous*/,
+                              const float* gg_grid /*[N,P,3]*/, const float* input,
+                              const int64_t* istr, const float* grid, const float* grad_output,
+                              float* grad_input /*zeroed*/, float* grad_grid,
+                              float* grad_grad_output, int N, int C, int D, int H, int W,
+                              int64_t P, cudaStream_t s);
+int sr_grid_sample3d_fwd_f64(const double* input, const int64_t* istr, const double* grid,
+                             double* output, int32_t* corner_idx, int N, int C, int D, int H,
+                             int W, int64_t P, cudaStream_t s);
+int sr_grid_sample3d_bwd_f64(const double* input, const int64_t* istr, const double* grid,
+                             const double* grad_output, double* grad_input, double* grad_grid,
+                             int N, int C, int D, int H, int W, int64_t P, cudaStream_t s);
+int sr_grid_sample3d_dbwd_f64(const double* gg_input, const double* gg_grid, const double* input,
+                              const int64_t* istr, const double* grid, const double* grad_output,
+                              double* grad_input, double* grad_grid, double* grad_grad_output,
+                              int N, int C, int D, int H, int W, int64_t P, cudaStream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused MLP stacks (positional encoding + all layers + activations in one kernel).
+ *
+ * A network is described by an sr_mlp_desc living in HOST memory (copied by value at
+ * launch).  Weights are passed pre-folded by sr_fold_linear: W_T[k][n] (k-major, n padded
+ * to a multiple of 128, k padded to a multiple of 8, zero filled), bias[n].
+ * Replaces ImplicitNetwork.forward/.gradient (model/network.py:72-114),
+ * MLPTranslator.forward (model/Deformer.py:49-76),
+ * RenderingNetwork_view_norm.forward (model/RenderNet.py:54-89) and the Embedder
+ * (model/Embedder.py:34-55, utils/utils.py:40-46).
+ * ------------------------------------------------------------------------------------------ */
+#define SR_MLP_MAX_LAYERS 12
+enum { SR_ACT_NONE = 0, SR_ACT_SOFTPLUS100 = 1, SR_ACT_RELU = 2, SR_ACT_TANH = 3 };
+
+typedef struct sr_mlp_layer {
+  const float* wt;   /* [kpad][npad] device */
+  const float* bias; /* [npad] device */
+  int k;             /* true fan-in (after skip concat) */
+  int n;             /* true fan-out */
+  int kpad;          /* multiple of 8, <= 512 */
+  int npad;          /* multiple of 128, <= 512 */
+  int act;           /* SR_ACT_* applied to this layer's output */
+  int skip;          /* 1: input = cat([x, net_input]) / sqrt(2) (network.py:88-89) */
+} sr_mlp_layer;
+
+typedef struct sr_mlp_desc {
+  int n_layers;
+  int d_in;          /* width of the embedded network input (39 / 167 / 289 ...) */
+  int multires;      /* PE bands on the 3-vector that is embedded */
+  float pe_w[16];    /* per-band annealing weights (utils/utils.py:40-46), one per band */
+  sr_mlp_layer layer[SR_MLP_MAX_LAYERS];
+} sr_mlp_desc;
+
+/* weight-norm fold + transpose + pad:  W = g * v / ||v||_row  (g == NULL -> W = v).
+ *   v: [n,k] row-major (torch nn.Linear.weight), g: [n] or NULL, b: [n] or NULL.
+ *   wt: [kpad][npad], bias_out: [npad].  (network.py:65-66, RenderNet.py:46-47) */
+int sr_fold_linear(const float* v, const float* g, const float* b, int n, int k, int npad,
+                   int kpad, float* wt, float* bias_out, cudaStream_t s);
+
+/* SDF network.  pts [P,3] -> sdf[P]; optional grad[P,3] (= d sdf / d pts, forward-mode),
+ * optional feat[P,nfeat] (outputs 1..nfeat of the last layer = `rendcond`).            */
+int sr_sdf_forward(const sr_mlp_desc* net, const float* pts, int64_t P, float* sdf, float* grad,
+                   float* feat, int nfeat, cudaStream_t s);
+
+/* Per-frame bone transforms for LBS: axis-angle -> rotation (batch_rodrigues,
+ * smpl_pytorch/util.py:35-68), kinematic chain and init-pose product
+ * (model/Deformer.py:176-203).  poses [F,24,3], Js [24,3], parents [24] int32,
+ * init_pose_inv [24,4,4] (or NULL: Deformer.py:196-200 branch) -> A [F,24,4,4].          */
+int sr_lbs_bone_transforms(const float* poses, const float* Js, const int32_t* parents,
+                           const float* init_pose_inv, int F, float* A, float* posedJ /*[F,24,3] or NULL*/,
+                           cudaStream_t s);
+
+typedef struct sr_lbs_params {
+  const float* ws_cl;   /* skin-weight volume, channels-last [D,H,W,24] device */
+  int D, H, W;
+  float bmin[3], bmax[3];
+  const float* A;       /* [F,24,4,4] from sr_lbs_bone_transforms */
+  const float* trans;   /* [F,3] */
+  int F;
+} sr_lbs_params;
+
+/* NCDHW [1,24,D,H,W] -> channels-last [D,H,W,24] (one-time / on-change re-layout). */
+int sr_lbs_weights_to_channels_last(const float* ws_ncdhw, float* ws_cl, int D, int H, int W,
+                                    cudaStream_t s);
+
+/* Composite deformer D(p) = LBS(p + MLPTranslator(p, cond[b])) (model/Deformer.py:15-20).
+ *   pts [P,3]; batch_inds [P] int64 or NULL (then b = i / pts_per_frame: "mesh mode");
+ *   conds [F,condlen]; lbs == NULL -> translator only.
+ *   out d[P,3]; optional offset[P,3] (MLPTranslator.offset), optional jac[P,3,3]
+ *   (= d D / d p, row r = gradient of output r: utils/utils.py:106-120), optional
+ *   corner_idx[P,3] int32 (LBS trilinear corner indices).                                 */
+int sr_deform_forward(const sr_mlp_desc* net, const sr_lbs_params* lbs, const float* pts,
+                      const int64_t* batch_inds, int64_t pts_per_frame, const float* conds,
+                      int condlen, int64_t P, float* d, float* offset, float* jac,
+                      int32_t* corner_idx, cudaStream_t s);
+
+/* Rendering network: cat([p, PE(view), n, feat]) -> rgb in [-1,1] (RenderNet.py:54-89). */
+int sr_render_forward(const sr_mlp_desc* net, const float* pts, const float* normals,
+                      const float* views, const float* feat, int nfeat, int64_t P, float* rgb,
+                      cudaStream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * Surface-point finder ("sphere tracer"), OptimizeSurfacePs (utils/FindSurfacePs.py:114-163).
+ * State arrays (device, caller allocated):
+ *   pts[P,3] in/out, rays[P,3], batch_inds[P] int64, active_a/active_b [P] int32 work lists,
+ *   counters[4] int32, converged[P] bytes (out).
+ * sr_trace_init evaluates the initial test and builds the first active list;
+ * sr_trace_iter performs ONE damped-Newton iteration on the active list (update + re-test)
+ * and writes the next list.  The host launches it `times` times back to back -- no host
+ * sync; an empty list makes the launch a no-op.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sr_trace_params {
+  float cam_pos[3];
+  float dthreshold;   /* |f| < dthreshold                       */
+  float athreshold;   /* angle (degrees) < athreshold           */
+  float w1, w2;       /* loss = w1*|f| + w2*sin(angle)          */
+} sr_trace_params;
+
+int sr_trace_step(const sr_mlp_desc* sdf, const sr_mlp_desc* dnet, const sr_lbs_params* lbs,
+                  const sr_trace_params* tp, float* pts, const float* rays,
+                  const int64_t* batch_inds, const float* conds, int condlen, int64_t P,
+                  const int32_t* active_in, int32_t* active_out, int32_t* counters, int iter,
+                  uint8_t* converged, cudaStream_t s);
+
+/* Geometry part of shading at converged points (infer path, model/network.py:356-361;
+ * utils/utils.py:155-169): n = normalize(grad f), cardinal ray = normalize(J^-1 v)
+ * (fallback v when |det J|<1e-4), feat = rendcond, d = D(p).                             */
+int sr_shade_geometry(const sr_mlp_desc* sdf, const sr_mlp_desc* dnet, const sr_lbs_params* lbs,
+                      const float* pts, const float* rays, const int64_t* batch_inds,
+                      const float* conds, int condlen, int64_t P, float* normals, float* crays,
+                      float* feat, int nfeat, float* dpos, uint8_t* inv_ok, cudaStream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * Coarse-to-fine SDF grid plumbing (Seg3dLossless, MCAcc/seg3d_lossless.py:266-372).
+ *   cand[z,y,x] = any(flag over the zero-padded 3x3x3 neighbourhood)
+ *                 && !calculated[z*sz, y*sy, x*sx]
+ *   flag/cand: [D,H,W] bytes (level lattice); calculated: [fD,fH,fW] bytes (final grid).
+ * Replaces the fp32 conv3d dilation (:296), the coords_accum masking (:299-301) and the
+ * 27-neighbour gathering of the conflict loop (:354-372).
+ * ------------------------------------------------------------------------------------------ */
+int sr_seg3d_candidates(const uint8_t* flag, const uint8_t* calculated, uint8_t* cand, int D,
+                        int H, int W, int sz, int sy, int sx, int fD, int fH, int fW,
+                        cudaStream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SELFRECON_B200_H_ */

@@ -1,0 +1,364 @@
+// Fused MLP tile engine (device side) -- SURVEY.md rows a1-a4, a8.
+//
+// One CTA evaluates a whole MLP stack for a tile of kTileRows "rows" without leaving the SM:
+// activations stay in shared memory (transposed, A_T[k][row]), the weights of each layer
+// are streamed k-slice by k-slice from L2 into a shared-memory ring by the TMA engine
+// (cp.async.bulk + mbarrier, issued by thread 0 one slice behind its own consumption), and 8
+// warps run a register-tiled fp32 FFMA GEMM (8 rows x 16 cols per thread).
+//
+// Rows are (point, channel) pairs: channel 0 carries the value, channels 1..T carry
+// forward-mode tangents d/dp_x, d/dp_y, d/dp_z, which share the layer GEMM with the value
+// and are multiplied by act'(z_value) in the epilogue.  With T=3 one pass yields f and
+// grad f (SDF) or the offset and its 3x3 Jacobian (deformer) -- no saved activations, no
+// transposed weights, no second kernel.
+//
+// All arithmetic is fp32 (the ray finder's convergence test is |f| < 5e-5, SURVEY.md
+// section 7 "hard parts"); this FFMA engine is the accuracy reference for the tcgen05
+// 3xTF32 variant planned next.
+#pragma once
+#include "common.cuh"
+
+namespace srmlp {
+
+constexpr int kTileRows = 64;          // rows per CTA tile
+constexpr int kRowStride = 68;         // A_T row stride in floats (64 + 4 pad)
+constexpr int kMaxK = 512;             // max fan-in (padded)
+constexpr int kMaxN = 512;             // max fan-out (padded)
+constexpr int kKT = 8;                 // k rows per pipeline stage
+constexpr int kStages = 4;             // weight ring depth
+constexpr int kStageFloats = kKT * kMaxN;
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumerThreads = kConsumerWarps * 32;
+// No dedicated producer warp: a 9th warp would put 3 warps on one SM sub-partition and cap
+// every thread at 168 registers (spills in the 8x16 accumulator tile).  Thread 0 issues the
+// TMA refills itself, one stage behind its own consumption (see Prod).
+constexpr int kThreads = kConsumerThreads;
+constexpr int kMaxIn = 296;            // max embedded input width kept in the stash (289 -> pad 8)
+constexpr int kStashMax = 40;          // skip-connection stash: PE(3 + 6*6) = 39 -> 40
+
+// Shared-memory carve-up (dynamic smem, 16-byte aligned pieces).
+struct Smem {
+  float* at;        // [kMaxK][kRowStride]
+  float* wring;     // [kStages][kStageFloats]
+  float* stash;     // [kStashMax][kRowStride]  embedded input kept for the skip layer
+  float* res;       // [kTileRows][8] last-layer outputs (cols 0..7) per row
+  uint64_t* full;   // [kStages]
+  uint64_t* empty;  // [kStages]
+};
+constexpr size_t kSmemBytes = (size_t)kMaxK * kRowStride * 4 + (size_t)kStages * kStageFloats * 4 +
+                              (size_t)kStashMax * kRowStride * 4 + (size_t)kTileRows * 8 * 4 +
+                              2 * kStages * 8 + 64;
+
+__device__ __forceinline__ Smem carve(unsigned char* base) {
+  Smem s;
+  s.at = reinterpret_cast<float*>(base);
+  base += (size_t)kMaxK * kRowStride * 4;
+  s.wring = reinterpret_cast<float*>(base);
+  base += (size_t)kStages * kStageFloats * 4;
+  s.stash = reinterpret_cast<float*>(base);
+  base += (size_t)kStashMax * kRowStride * 4;
+  s.res = reinterpret_cast<float*>(base);
+  base += (size_t)kTileRows * 8 * 4;
+  s.full = reinterpret_cast<uint64_t*>(base);
+  s.empty = s.full + kStages;
+  return s;
+}
+
+// Ring position shared (by construction, not by memory) between producer and consumers:
+// both walk exactly the same (tile, net, layer, k-slice) sequence.
+struct Pipe {
+  int slot;
+  uint32_t phase;
+  __device__ __forceinline__ void advance() {
+    if (++slot == kStages) { slot = 0; phase ^= 1u; }
+  }
+};
+
+__device__ __forceinline__ void pipe_init(const Smem& s) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      sr_mbar_init(&s.full[i], 1);
+      sr_mbar_init(&s.empty[i], kConsumerWarps);
+    }
+    sr_fence_barrier_init();
+  }
+  __syncthreads();
+}
+
+// all-consumer barrier (named barrier 1; barrier 0 is left to __syncthreads)
+__device__ __forceinline__ void consumer_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Producer cursor (meaningful in thread 0 only): walks tiles x nets x layers x k-slices and
+// issues one bulk copy per call.  kStages-1 slices are issued up front; afterwards thread 0
+// issues one more each time its warp has finished a slice, so the slot it waits for is the
+// one every warp finished a full slice ago (loose coupling, 3 slices in flight).
+// ---------------------------------------------------------------------------------------------
+struct Prod {
+  Pipe pp;
+  long long tile, ntiles;
+  int stride, net_i, layer, slice, nnets;
+  const sr_mlp_desc* nets[2];
+  bool done;
+  __device__ __forceinline__ void init(long long first_tile, long long ntiles_, int stride_,
+                                       const sr_mlp_desc* n0, const sr_mlp_desc* n1) {
+    pp.slot = 0; pp.phase = 0;
+    tile = first_tile; ntiles = ntiles_; stride = stride_;
+    net_i = 0; layer = 0; slice = 0;
+    nets[0] = n0; nets[1] = n1; nnets = n1 ? 2 : 1;
+    done = first_tile >= ntiles_;
+  }
+  __device__ __forceinline__ void issue(const Smem& s) {
+    if (done) return;
+    const sr_mlp_desc* net = nets[net_i];
+    const sr_mlp_layer& L = net->layer[layer];
+    const uint32_t bytes = (uint32_t)(kKT * L.npad * 4);
+    sr_mbar_wait(&s.empty[pp.slot], pp.phase ^ 1u);
+    sr_mbar_arrive_expect_tx(&s.full[pp.slot], bytes);
+    sr_bulk_g2s(s.wring + (size_t)pp.slot * kStageFloats,
+                reinterpret_cast<const char*>(L.wt) + (size_t)slice * bytes, bytes,
+                &s.full[pp.slot]);
+    pp.advance();
+    if (++slice == L.kpad / kKT) {
+      slice = 0;
+      if (++layer == net->n_layers) {
+        layer = 0;
+        if (++net_i == nnets) {
+          net_i = 0;
+          tile += stride;
+          if (tile >= ntiles) done = true;
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void prefill(const Smem& s) {
+    if (threadIdx.x == 0)
+      for (int i = 0; i < kStages - 1; ++i) issue(s);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Activations
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float softplus100(float z, float& deriv) {
+  // torch.nn.Softplus(beta=100, threshold=20) and its autograd formula
+  const float bz = z * 100.0f;
+  if (bz > 20.0f) { deriv = 1.0f; return z; }
+  const float e = expf(bz);
+  deriv = e / (e + 1.0f);
+  return log1pf(e) / 100.0f;
+}
+__device__ __forceinline__ float apply_act(int act, float z, float& deriv) {
+  switch (act) {
+    case SR_ACT_SOFTPLUS100: return softplus100(z, deriv);
+    case SR_ACT_RELU: deriv = z > 0.0f ? 1.0f : 0.0f; return z > 0.0f ? z : 0.0f;
+    case SR_ACT_TANH: { const float t = tanhf(z); deriv = 1.0f - t * t; return t; }
+    default: deriv = 1.0f; return z;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One layer: acc[8][4G] = A_T[0:kpad][rows]^T * W_T[0:kpad][cols]
+//   thread (warp w, lane l) owns rows 8w..8w+7 and cols { g*128 + 4*l + i }.
+// ---------------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ void layer_gemm(const Smem& s, Pipe& cp, Prod& prod, int kpad,
+                                           int npad, float (&acc)[8][16]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[r][c] = 0.0f;
+  const float* arow = s.at + 8 * warp;
+  const int nslices = kpad / kKT;
+  for (int sl = 0; sl < nslices; ++sl) {
+    sr_mbar_wait(&s.full[cp.slot], cp.phase);
+    const float* wst = s.wring + (size_t)cp.slot * kStageFloats + 4 * lane;
+    const float* ak = arow + (size_t)sl * kKT * kRowStride;
+#pragma unroll
+    for (int kk = 0; kk < kKT; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(ak + kk * kRowStride);
+      const float4 a1 = *reinterpret_cast<const float4*>(ak + kk * kRowStride + 4);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wst + kk * npad + g * 128);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          acc[r][4 * g + 0] = fmaf(a[r], w4.x, acc[r][4 * g + 0]);
+          acc[r][4 * g + 1] = fmaf(a[r], w4.y, acc[r][4 * g + 1]);
+          acc[r][4 * g + 2] = fmaf(a[r], w4.z, acc[r][4 * g + 2]);
+          acc[r][4 * g + 3] = fmaf(a[r], w4.w, acc[r][4 * g + 3]);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) sr_mbar_arrive(&s.empty[cp.slot]);
+    if (threadIdx.x == 0) prod.issue(s);
+    cp.advance();
+  }
+}
+
+// Epilogue: bias + activation (+ tangent scaling), result back into A_T as the next layer's
+// input, or -- for the last layer -- into s.res (cols < 8) and optionally a global feature
+// buffer.  T = number of tangent channels (0 or 3): rows r of a thread are
+//   T=0: 8 points;   T=3: 2 points x {value, d/dx, d/dy, d/dz}.
+struct LastOut {
+  float* feat;        // global [P][nfeat] or nullptr: cols 1..nfeat of value rows
+  int nfeat;
+  const int* row_pt;  // smem: global point index per tile-local point (or -1)
+};
+
+template <int G, int T>
+__device__ __forceinline__ void layer_epilogue(const Smem& s, const sr_mlp_layer& L, bool last,
+                                               bool next_skip, int next_kpad, int d_in,
+                                               const LastOut& lo, float (&acc)[8][16]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int CH = T + 1;
+  constexpr int PPT = 8 / CH;  // points per thread
+  const float inv_div = 1.41421356237309504880f;  // np.sqrt(2) rounded to fp32
+  // (1) every warp must be done reading A_T before anyone overwrites it
+  consumer_sync();
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = 4 * g + i;
+      const int col = g * 128 + 4 * lane + i;
+      if (col < L.n) {
+        const float b = __ldg(L.bias + col);
+        float o[8];
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {
+          float d;
+          const float z = acc[p * CH][c] + b;
+          o[p * CH] = apply_act(L.act, z, d);
+#pragma unroll
+          for (int t = 1; t < CH; ++t) o[p * CH + t] = d * acc[p * CH + t][c];
+        }
+        if (!last) {
+          if (next_skip) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) o[r] = __fdiv_rn(o[r], inv_div);
+          }
+          float* dst = s.at + (size_t)col * kRowStride + 8 * warp;
+          *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        } else {
+          if (col < 8) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) s.res[(8 * warp + r) * 8 + col] = o[r];
+          }
+          if (lo.feat != nullptr && col >= 1 && col <= lo.nfeat) {
+#pragma unroll
+            for (int p = 0; p < PPT; ++p) {
+              const int gp = lo.row_pt[(8 * warp) / CH + p];
+              if (gp >= 0) lo.feat[(size_t)gp * lo.nfeat + (col - 1)] = o[p * CH];
+            }
+          }
+        }
+      } else if (!last) {
+        // zero the k-padding rows the next layer will multiply by zero weights
+        const int lim = next_skip ? 0 : next_kpad;  // (skip case handled below)
+        if (col < lim) {
+          float* dst = s.at + (size_t)col * kRowStride + 8 * warp;
+          *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+  }
+  if (!last && next_skip) {
+    // x = cat([x, input]) / sqrt(2): append the stashed embedded input (model/network.py:88-89)
+    for (int idx = threadIdx.x; idx < (next_kpad - L.n) * (kTileRows / 4); idx += kConsumerThreads) {
+      const int kk = idx / (kTileRows / 4), r4 = (idx % (kTileRows / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kk < d_in) {
+        v = *reinterpret_cast<const float4*>(s.stash + (size_t)kk * kRowStride + r4);
+        v.x = __fdiv_rn(v.x, inv_div); v.y = __fdiv_rn(v.y, inv_div);
+        v.z = __fdiv_rn(v.z, inv_div); v.w = __fdiv_rn(v.w, inv_div);
+      }
+      *reinterpret_cast<float4*>(s.at + (size_t)(L.n + kk) * kRowStride + r4) = v;
+    }
+  }
+  // (2) next layer's reads must see the writes
+  consumer_sync();
+}
+
+// Runs all layers of `net` on the tile whose embedded input is already in A_T rows
+// [0, layer[0].kpad) (and in the stash when the net has a skip layer).
+template <int T>
+__device__ __forceinline__ void run_net(const sr_mlp_desc& net, const Smem& s, Pipe& cp,
+                                        Prod& prod, const LastOut& lo) {
+  float acc[8][16];
+  for (int l = 0; l < net.n_layers; ++l) {
+    const sr_mlp_layer& L = net.layer[l];
+    const bool last = (l == net.n_layers - 1);
+    const bool next_skip = !last && net.layer[l + 1].skip != 0;
+    const int next_kpad = last ? 0 : net.layer[l + 1].kpad;
+    switch (L.npad >> 7) {
+      case 1:
+        layer_gemm<1>(s, cp, prod, L.kpad, L.npad, acc);
+        layer_epilogue<1, T>(s, L, last, next_skip, next_kpad, net.d_in, lo, acc);
+        break;
+      case 2:
+        layer_gemm<2>(s, cp, prod, L.kpad, L.npad, acc);
+        layer_epilogue<2, T>(s, L, last, next_skip, next_kpad, net.d_in, lo, acc);
+        break;
+      case 3:
+        layer_gemm<3>(s, cp, prod, L.kpad, L.npad, acc);
+        layer_epilogue<3, T>(s, L, last, next_skip, next_kpad, net.d_in, lo, acc);
+        break;
+      default:
+        layer_gemm<4>(s, cp, prod, L.kpad, L.npad, acc);
+        layer_epilogue<4, T>(s, L, last, next_skip, next_kpad, net.d_in, lo, acc);
+        break;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Positional encoding of a 3-vector into A_T rows [k0, k0 + 3 + 6*L) for tile row `row`
+// (value channel) and, if T=3, its three tangent rows (row+1..row+3).
+//   layout (model/Embedder.py:11-32): [x, sin(2^0 x), cos(2^0 x), sin(2^1 x), cos(2^1 x), ...]
+//   each block 3 wide; band weights w_b (utils/utils.py:40-46) multiply sin and cos.
+// ---------------------------------------------------------------------------------------------
+template <int T>
+__device__ __forceinline__ void embed_point(float* dst, int k0, int row, const float x[3],
+                                            int multires, const float* pe_w, bool tangent_unit) {
+  // value row
+#pragma unroll
+  for (int j = 0; j < 3; ++j) dst[(size_t)(k0 + j) * kRowStride + row] = x[j];
+  if (T == 3) {
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        dst[(size_t)(k0 + j) * kRowStride + row + 1 + t] = (tangent_unit && t == j) ? 1.0f : 0.0f;
+  }
+  float freq = 1.0f;
+  for (int b = 0; b < multires; ++b, freq *= 2.0f) {
+    const float w = pe_w[b];
+    const int ks = k0 + 3 + 6 * b, kc = ks + 3;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float arg = x[j] * freq;
+      float sn, cs;
+      sincosf(arg, &sn, &cs);
+      dst[(size_t)(ks + j) * kRowStride + row] = w * sn;
+      dst[(size_t)(kc + j) * kRowStride + row] = w * cs;
+      if (T == 3) {
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          const bool on = tangent_unit && (t == j);
+          dst[(size_t)(ks + j) * kRowStride + row + 1 + t] = on ? (w * freq) * cs : 0.0f;
+          dst[(size_t)(kc + j) * kRowStride + row + 1 + t] = on ? -(w * freq) * sn : 0.0f;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace srmlp

@@ -1,0 +1,134 @@
+"""Coarse-to-fine evaluation of an implicit function on a dense grid
+(reference: MCAcc/seg3d_lossless.py:13-428, Seg3dLossless._forward).
+
+Same constructor, public attributes (query_func, balance_value, spacing_x/y/z, bx/by/bz, b_min,
+b_max, resolutions) and result ([1,1,D,H,W] float grid at the finest resolution) as the
+reference.  The algorithm is the reference's: evaluate the coarsest lattice, then per level
+upsample 2x-1, find lattice points whose surrounding coarse values disagree on `> balance`,
+dilate by one, drop what was already evaluated, query the function there, and repair sign
+conflicts by querying the 27-neighbourhoods until none remain.  The plumbing differs:
+
+  * upsample + boundary flag: one kernel (csrc/interp2x.cu) instead of two F.interpolate calls;
+  * dilation + "already evaluated" mask: one byte kernel (csrc/seg3d.cu) over the strided view
+    of the final-grid `calculated` mask -- the reference keeps a coordinate list made unique by a
+    sort at every step (seg3d_lossless.py:343-346) and dilates with an fp32 conv3d (:296);
+  * the query function receives the same points, in lattice (z,y,x) order rather than the
+    reference's (x,y,z) order; values are scattered back by index, so the grid is identical.
+"""
+import torch
+import torch.nn as nn
+
+from selfreconcode_b200 import ops
+from .utils import create_grid3D, SmoothConv3D
+
+
+class Seg3dLossless(nn.Module):
+    def __init__(self, query_func, b_min, b_max, resolutions, channels=1, balance_value=0.5,
+                 align_corners=False, visualize=False, debug=False, use_cuda_impl=False,
+                 faster=False, use_shadow=False, **kwargs):
+        super().__init__()
+        self.query_func = query_func
+        b_min = b_min if torch.is_tensor(b_min) else torch.tensor(b_min)
+        b_max = b_max if torch.is_tensor(b_max) else torch.tensor(b_max)
+        self.register_buffer('b_min', b_min.float().view(1, 1, 3))
+        self.register_buffer('b_max', b_max.float().view(1, 1, 3))
+        if type(resolutions[0]) is int:
+            resolutions = torch.tensor([(res, res, res) for res in resolutions])
+        else:
+            resolutions = torch.tensor(resolutions)
+        self.register_buffer('resolutions', resolutions)
+        tmp = (self.b_max.view(3) - self.b_min.view(3)) / self.resolutions[-1].view(3).float()
+        self.spacing_x, self.spacing_y, self.spacing_z = tmp[0].item(), tmp[1].item(), tmp[2].item()
+        self.bx = self.b_min.view(-1)[0].item() + self.spacing_x / 2.
+        self.by = self.b_min.view(-1)[1].item() + self.spacing_y / 2.
+        self.bz = self.b_min.view(-1)[2].item() + self.spacing_z / 2.
+        self.batchsize = self.b_min.size(0)
+        assert self.batchsize == 1
+        self.balance_value = balance_value
+        self.channels = channels
+        assert self.channels == 1
+        self.align_corners = align_corners
+        assert align_corners == False
+        self.visualize = visualize
+        assert visualize == False
+        self.debug = debug
+        self.use_cuda_impl = use_cuda_impl  # accepted for API parity; the kernels are always used
+        self.faster = faster
+        self.use_shadow = use_shadow
+        if use_shadow:
+            raise NotImplementedError("use_shadow is never enabled by the reference's drivers")
+        for resolution in resolutions:
+            assert resolution[0] % 2 == 1 and resolution[1] % 2 == 1, \
+                f"resolution {resolution} need to be odd becuase of align_corner."
+        init_coords = create_grid3D(0, resolutions[-1] - 1, steps=resolutions[0], device="cpu")
+        self.register_buffer('init_coords', init_coords.unsqueeze(0))
+        self.last_num_queried = 0
+
+    # MCAcc/seg3d_lossless.py:89-108
+    def batch_eval(self, coords, **kwargs):
+        coords = coords.detach()
+        step = 1.0 / self.resolutions[-1].float()
+        coords2D = coords.float() / self.resolutions[-1] + step / 2
+        coords2D = coords2D * (self.b_max - self.b_min) + self.b_min
+        occupancys = self.query_func(**kwargs, points=coords2D)
+        if type(occupancys) is list:
+            occupancys = torch.stack(occupancys)
+        assert len(occupancys.size()) == 3, \
+            "query_func should return a occupancy with shape of [bz, C, N]"
+        return occupancys
+
+    def forward(self, **kwargs):
+        return self._forward(**kwargs)
+
+    def _lattice_coords(self, lin, H, W, stride):
+        z = lin // (H * W)
+        y = (lin // W) % H
+        x = lin % W
+        return torch.stack([x * stride[0], y * stride[1], z * stride[2]], dim=1).unsqueeze(0)
+
+    def _forward(self, **kwargs):
+        dev = self.b_min.device
+        if dev.type != "cuda":
+            raise RuntimeError("Seg3dLossless: module must live on a CUDA device (no CPU path)")
+        fW, fH, fD = [int(v) for v in self.resolutions[-1]]
+        calculated = torch.zeros((fD, fH, fW), dtype=torch.bool, device=dev)
+        bal = self.balance_value
+        nq = 0
+        occ = None
+        for li, resolution in enumerate(self.resolutions):
+            W, H, D = [int(v) for v in resolution]
+            stride = (self.resolutions[-1] - 1) // (resolution - 1)  # (sx, sy, sz)
+            sx, sy, sz = [int(v) for v in stride]
+            stride_dev = stride.to(dev)
+            if li == 0:
+                coords = self.init_coords.clone()
+                occ = self.batch_eval(coords, **kwargs).view(D, H, W).float()
+                c = coords[0]
+                calculated[c[:, 2], c[:, 1], c[:, 0]] = True
+                nq += c.shape[0]
+                continue
+            up, is_b = ops.interp2x3d_forward(occ.view(1, 1, *occ.shape).contiguous(), bal)
+            occ = up[0, 0]
+            assert occ.shape == (D, H, W)
+            flag = is_b[0, 0]
+            flat = occ.view(-1)
+            while True:
+                cand = ops.seg3d_candidates(flag, calculated, (sz, sy, sx))
+                lin = cand.view(-1).nonzero().view(-1)
+                if lin.numel() == 0:
+                    break
+                coords = self._lattice_coords(lin, H, W, stride_dev)
+                interp = flat[lin]
+                true = self.batch_eval(coords, **kwargs).view(-1).float()
+                flat[lin] = true
+                c = coords[0]
+                calculated[c[:, 2], c[:, 1], c[:, 0]] = True
+                nq += lin.numel()
+                conflicts = (interp - bal) * (true - bal) < 0
+                if not bool(conflicts.any()):
+                    break
+                flag = torch.zeros((D * H * W,), dtype=torch.bool, device=dev)
+                flag[lin[conflicts]] = True
+                flag = flag.view(D, H, W)
+        self.last_num_queried = nq
+        return occ.view(1, 1, *occ.shape)

@@ -1,0 +1,159 @@
+"""Neural SDF (reference: model/network.py:14-118) on the fused B200 engine.
+
+`ImplicitNetwork` keeps the reference's constructor signature, initialisation, attribute names
+and state_dict keys (lin{l}.weight_g / weight_v / bias), and the `rendcond` side effect of
+forward().  Execution:
+  * no autograd needed (tracing, MC queries, inference): one fused kernel per call
+    (csrc/mlp_kernels.cu: sdf_kernel) -- PE, all layers, softplus, optional grad f.
+  * autograd needed (training losses with create_graph): the same math as differentiable
+    torch ops on the GPU.  (Fused backward kernels are the next step; see DESIGN.md.)
+CPU tensors are rejected: there is no CPU path.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from selfreconcode_b200 import ops
+from .Embedder import get_embedder
+from ._fused import (FoldCache, needs_autograd, ratio_value, require_cuda, SR_ACT_NONE,
+                     SR_ACT_SOFTPLUS100)
+
+
+class ImplicitNetwork(nn.Module):
+    def __init__(self, feature_vector_size, d_in, d_out, dims, geometric_init=True, bias=1.0,
+                 skip_in=(), weight_norm=True, multires=0):
+        super().__init__()
+        dims = [d_in] + list(dims) + [d_out + feature_vector_size]
+        self.d_out = d_out
+        self.embed_fn = None
+        self.multires = multires
+        if multires > 0:
+            self.embed_fn, dims[0] = get_embedder(multires)
+        self.num_layers = len(dims)
+        self.skip_in = skip_in
+        self.weight_norm = weight_norm
+        for l in range(self.num_layers - 1):
+            out_dim = dims[l + 1] - dims[0] if (l + 1) in self.skip_in else dims[l + 1]
+            lin = nn.Linear(dims[l], out_dim)
+            if geometric_init:  # IGR / IDR geometric initialisation (network.py:49-63)
+                if l == self.num_layers - 2:
+                    nn.init.normal_(lin.weight, mean=np.sqrt(np.pi) / np.sqrt(dims[l]), std=0.0001)
+                    nn.init.constant_(lin.bias, -bias)
+                elif multires > 0 and l == 0:
+                    nn.init.constant_(lin.bias, 0.0)
+                    nn.init.constant_(lin.weight[:, 3:], 0.0)
+                    nn.init.normal_(lin.weight[:, :3], 0.0, np.sqrt(2) / np.sqrt(out_dim))
+                elif multires > 0 and l in self.skip_in:
+                    nn.init.constant_(lin.bias, 0.0)
+                    nn.init.normal_(lin.weight, 0.0, np.sqrt(2) / np.sqrt(out_dim))
+                    nn.init.constant_(lin.weight[:, -(dims[0] - 3):], 0.0)
+                else:
+                    nn.init.constant_(lin.bias, 0.0)
+                    nn.init.normal_(lin.weight, 0.0, np.sqrt(2) / np.sqrt(out_dim))
+            if weight_norm:
+                lin = nn.utils.weight_norm(lin)
+            setattr(self, "lin" + str(l), lin)
+        self.softplus = nn.Softplus(beta=100)
+        self.rendcond = None
+        self._cache = FoldCache()
+
+    # ---- fused engine --------------------------------------------------------------------
+    def _layers(self):
+        out = []
+        for l in range(self.num_layers - 1):
+            lin = getattr(self, "lin" + str(l))
+            if self.weight_norm:
+                v, g = lin.weight_v, lin.weight_g
+            else:
+                v, g = lin.weight, None
+            out.append(dict(v=v, g=g, b=lin.bias,
+                            act=SR_ACT_SOFTPLUS100 if l < self.num_layers - 2 else SR_ACT_NONE,
+                            skip=(l in self.skip_in)))
+        return out
+
+    def fused(self):
+        layers = self._layers()
+        params = [t for L in layers for t in (L["v"], L["g"], L["b"]) if t is not None]
+        dev = params[0].device
+        require_cuda(params[0], "ImplicitNetwork")
+        if self.multires <= 0:
+            raise RuntimeError("ImplicitNetwork: the fused engine expects multires > 0")
+
+        def build():
+            return ops.FusedMLP(3 + 6 * self.multires, self.multires, dev).fold(layers)
+
+        return self._cache.get(params, build)
+
+    def fused_sdf_only(self):
+        net = self.fused()
+        ex = self._cache.extra
+        if "sdf_only" not in ex:
+            ex["sdf_only"] = net.truncated_last(self.d_out)
+        return ex["sdf_only"]
+
+    def _pe_weights(self, ratio):
+        return ops.annealing_weights(self.multires, ratio)
+
+    def forward_fused(self, input, ratio, want_grad=False, want_feat=True):
+        """-> (sdf [P,d_out], grad [P,3] | None, feat | None) without building a graph."""
+        if self.d_out != 1:
+            raise RuntimeError("ImplicitNetwork: fused path supports d_out == 1")
+        r = ratio_value(ratio, "sdfRatio")
+        nlast = getattr(self, "lin" + str(self.num_layers - 2)).bias.shape[0]
+        nfeat = nlast - self.d_out if want_feat else 0
+        net = self.fused() if nfeat > 0 else self.fused_sdf_only()
+        w = self._pe_weights(r)
+        net.set_pe_weights(w)
+        sdf, grad, feat = ops.sdf_forward(net, input.detach().reshape(-1, 3), want_grad, nfeat)
+        return sdf.view(-1, 1), grad, feat
+
+    # ---- reference surface ---------------------------------------------------------------
+    def forward(self, input, ratio):
+        require_cuda(input, "ImplicitNetwork.forward")
+        params_need = any(p.requires_grad for p in self.parameters())
+        if not needs_autograd(input) and not (torch.is_grad_enabled() and params_need):
+            sdf, _, feat = self.forward_fused(input, ratio, False, True)
+            self.rendcond = feat
+            return sdf
+        return self._forward_autograd(input, ratio)
+
+    def _forward_autograd(self, input, ratio):
+        ratio = ratio_value(ratio, "sdfRatio")
+        if self.embed_fn is not None:
+            if ratio is None:
+                input = self.embed_fn(input)
+            elif ratio <= 0:
+                input = self.embed_fn(input, [0.0] * (self.multires * 2))
+            else:
+                ws = [w for w in self._pe_weights(ratio) for _ in (0, 1)]
+                input = self.embed_fn(input, ws)
+        x = input
+        for l in range(self.num_layers - 1):
+            lin = getattr(self, "lin" + str(l))
+            if l in self.skip_in:
+                x = torch.cat([x, input], 1) / np.sqrt(2)
+            x = lin(x)
+            if l < self.num_layers - 2:
+                x = self.softplus(x)
+        if x.shape[-1] > self.d_out:
+            self.rendcond = x[:, self.d_out:]
+            x = x[:, 0:self.d_out]
+        else:
+            self.rendcond = None
+        return x
+
+    def gradient(self, x, y=None):
+        x.requires_grad_(True)
+        if y is None:
+            y = self.forward(x)
+        d_output = torch.ones_like(y, requires_grad=False, device=y.device)
+        gradients = torch.autograd.grad(outputs=y, inputs=x, grad_outputs=d_output,
+                                        create_graph=True, retain_graph=True, only_inputs=True)[0]
+        return gradients.view(-1, 3)
+
+
+def getTmpSdf(device, multires, bias=0.6, feature_vector_size=256):
+    net = ImplicitNetwork(feature_vector_size=feature_vector_size, d_in=3, d_out=1,
+                          dims=[512] * 8, geometric_init=True, bias=bias, skip_in=[4],
+                          weight_norm=True, multires=multires)
+    return net.to(device)

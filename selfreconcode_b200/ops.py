@@ -1,0 +1,481 @@
+"""Torch-facing wrappers over the C ABI (include/selfrecon_b200.h).
+
+torch is plumbing here: it owns device memory and the current stream; every computation is a
+call into libselfrecon_b200.so.  All functions require CUDA tensors and raise otherwise --
+there is no CPU path in the product (the CPU restatement lives in oracle/ and is only used
+by tests and bench baselines).
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import MlpDesc, LbsParams, TraceParams, check
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("selfrecon_b200: expected a CUDA tensor (no CPU fallback)")
+
+
+# ------------------------------------------------------------------------------------------------
+# FastMinv  (FastMinv/M3x3Inv.cpp:12-59)
+# ------------------------------------------------------------------------------------------------
+def minv3x3(ms):
+    _need_cuda(ms)
+    n = ms.shape[0]
+    invs = torch.empty((n, 3, 3), dtype=ms.dtype, device=ms.device)
+    checks = torch.empty((n,), dtype=torch.bool, device=ms.device)
+    lib = _lib.load()
+    with torch.cuda.device(ms.device):
+        fn = lib.sr_minv3x3_f32 if ms.dtype == torch.float32 else lib.sr_minv3x3_f64
+        check(fn(_p(ms), _p(invs), _p(checks), n, _stream()), "minv3x3")
+    return invs, checks
+
+
+def minv3x3_backward(grads, invs):
+    _need_cuda(grads, invs)
+    n = invs.shape[0]
+    outs = torch.empty((n, 3, 3), dtype=invs.dtype, device=invs.device)
+    lib = _lib.load()
+    with torch.cuda.device(invs.device):
+        fn = lib.sr_minv3x3_bwd_f32 if invs.dtype == torch.float32 else lib.sr_minv3x3_bwd_f64
+        check(fn(_p(grads), _p(invs), _p(outs), n, _stream()), "minv3x3_bwd")
+    return outs
+
+
+# ------------------------------------------------------------------------------------------------
+# Marching cubes (MCGpu/MCGpu.cpp:20-56)
+# ------------------------------------------------------------------------------------------------
+_mc_work = {}
+
+
+def marching_cubes(sdfs, xstep=1.0, ystep=1.0, zstep=1.0, xmin=0.0, ymin=0.0, zmin=0.0, iso=0.0):
+    """sdfs [NX,NY,NZ] f32 contiguous CUDA -> (vertices [V,3] f32, faces [F,3] i64), canonical
+    (deterministic) order.  One device->host read of the two counters, like the reference."""
+    _need_cuda(sdfs)
+    nx, ny, nz = sdfs.shape
+    lib = _lib.load()
+    dev = sdfs.device
+    with torch.cuda.device(dev):
+        wb = lib.sr_mc_work_bytes(nx, ny, nz)
+        key = (dev.index, torch.cuda.current_stream().cuda_stream)
+        work = _mc_work.get(key)
+        if work is None or work.numel() < wb:
+            work = torch.empty((wb,), dtype=torch.uint8, device=dev)
+            _mc_work[key] = work  # grows monotonically, like the reference's per-device scratch
+        counts = torch.empty((2,), dtype=torch.int32, device=dev)
+        check(lib.sr_mc_count(_p(sdfs), nx, ny, nz, float(iso), _p(work), _p(counts), _stream()),
+              "mc_count")
+        nv, nf = counts.tolist()  # the one blocking read-back
+        verts = torch.empty((nv, 3), dtype=torch.float32, device=dev)
+        faces = torch.empty((nf, 3), dtype=torch.int64, device=dev)
+        if nv or nf:
+            check(lib.sr_mc_emit(_p(sdfs), nx, ny, nz, float(iso), float(xstep), float(ystep),
+                                 float(zstep), float(xmin), float(ymin), float(zmin), _p(work),
+                                 _p(verts), nv, _p(faces), nf, _stream()), "mc_emit")
+    return verts, faces
+
+
+# ------------------------------------------------------------------------------------------------
+# interp2x_boundary  (MCAcc/cuda/interp2x_boundary3d.cpp:17-36)
+# ------------------------------------------------------------------------------------------------
+def interp2x3d_forward(inp, balance):
+    _need_cuda(inp)
+    b, c, d, h, w = inp.shape
+    out = torch.empty((b, c, 2 * d - 1, 2 * h - 1, 2 * w - 1), dtype=inp.dtype, device=inp.device)
+    bnd = torch.empty(out.shape, dtype=torch.bool, device=inp.device)
+    lib = _lib.load()
+    with torch.cuda.device(inp.device):
+        check(lib.sr_interp2x3d_fwd_f32(_p(inp), _p(out), _p(bnd), b * c, d, h, w, float(balance),
+                                        _stream()), "interp2x3d_fwd")
+    return out, bnd
+
+
+def interp2x3d_backward(grad_out):
+    _need_cuda(grad_out)
+    b, c, od, oh, ow = grad_out.shape
+    d, h, w = (od + 1) // 2, (oh + 1) // 2, (ow + 1) // 2
+    gin = torch.empty((b, c, d, h, w), dtype=grad_out.dtype, device=grad_out.device)
+    lib = _lib.load()
+    with torch.cuda.device(grad_out.device):
+        check(lib.sr_interp2x3d_bwd_f32(_p(grad_out), _p(gin), b * c, d, h, w, _stream()),
+              "interp2x3d_bwd")
+    return gin
+
+
+def interp2x2d_forward(inp, balance):
+    _need_cuda(inp)
+    b, c, h, w = inp.shape
+    out = torch.empty((b, c, 2 * h - 1, 2 * w - 1), dtype=inp.dtype, device=inp.device)
+    bnd = torch.empty(out.shape, dtype=torch.bool, device=inp.device)
+    lib = _lib.load()
+    with torch.cuda.device(inp.device):
+        check(lib.sr_interp2x2d_fwd_f32(_p(inp), _p(out), _p(bnd), b * c, h, w, float(balance),
+                                        _stream()), "interp2x2d_fwd")
+    return out, bnd
+
+
+def interp2x2d_backward(grad_out):
+    _need_cuda(grad_out)
+    b, c, oh, ow = grad_out.shape
+    h, w = (oh + 1) // 2, (ow + 1) // 2
+    gin = torch.empty((b, c, h, w), dtype=grad_out.dtype, device=grad_out.device)
+    lib = _lib.load()
+    with torch.cuda.device(grad_out.device):
+        check(lib.sr_interp2x2d_bwd_f32(_p(grad_out), _p(gin), b * c, h, w, _stream()),
+              "interp2x2d_bwd")
+    return gin
+
+
+# ------------------------------------------------------------------------------------------------
+# GridSamplerMine  (MCAcc/cuda/GridSamplerMine.cpp:73-96)
+# ------------------------------------------------------------------------------------------------
+def _istr(t):
+    return (C.c_int64 * 5)(*t.stride())
+
+
+def _gs_suffix(t):
+    if t.dtype == torch.float32:
+        return "f32"
+    if t.dtype == torch.float64:
+        return "f64"
+    raise RuntimeError("grid_sampler_3d: only float32/float64 are supported")
+
+
+def grid_sample3d_forward(inp, grid, want_corner_idx=False):
+    _need_cuda(inp, grid)
+    N, Cc, D, H, W = inp.shape
+    Do, Ho, Wo = grid.shape[1:4]
+    P = Do * Ho * Wo
+    g = grid.reshape(N, P, 3).contiguous()
+    out = torch.empty((N, Cc, Do, Ho, Wo), dtype=inp.dtype, device=inp.device)
+    cidx = torch.empty((N, P, 3), dtype=torch.int32, device=inp.device) if want_corner_idx else None
+    lib = _lib.load()
+    with torch.cuda.device(inp.device):
+        fn = getattr(lib, "sr_grid_sample3d_fwd_" + _gs_suffix(inp))
+        check(fn(_p(inp), _istr(inp), _p(g), _p(out), _p(cidx), N, Cc, D, H, W, P, _stream()),
+              "grid_sample3d_fwd")
+    return (out, cidx) if want_corner_idx else out
+
+
+def grid_sample3d_backward(inp, grid, grad_output):
+    _need_cuda(inp, grid, grad_output)
+    N, Cc, D, H, W = inp.shape
+    Do, Ho, Wo = grid.shape[1:4]
+    P = Do * Ho * Wo
+    g = grid.reshape(N, P, 3).contiguous()
+    go = grad_output.reshape(N, Cc, P).contiguous()
+    ginp = torch.zeros((N, Cc, D, H, W), dtype=inp.dtype, device=inp.device)
+    ggrid = torch.empty((N, P, 3), dtype=inp.dtype, device=inp.device)
+    lib = _lib.load()
+    with torch.cuda.device(inp.device):
+        fn = getattr(lib, "sr_grid_sample3d_bwd_" + _gs_suffix(inp))
+        check(fn(_p(inp), _istr(inp), _p(g), _p(go), _p(ginp), _p(ggrid), N, Cc, D, H, W, P,
+                 _stream()), "grid_sample3d_bwd")
+    return ginp, ggrid.reshape(grid.shape)
+
+
+def grid_sample3d_dbackward(gg_input, gg_grid, inp, grid, grad_output):
+    _need_cuda(gg_input, gg_grid, inp, grid, grad_output)
+    N, Cc, D, H, W = inp.shape
+    Do, Ho, Wo = grid.shape[1:4]
+    P = Do * Ho * Wo
+    g = grid.reshape(N, P, 3).contiguous()
+    go = grad_output.reshape(N, Cc, P).contiguous()
+    ggi = gg_input.contiguous()
+    ggg = gg_grid.reshape(N, P, 3).contiguous()
+    ginp = torch.zeros((N, Cc, D, H, W), dtype=inp.dtype, device=inp.device)
+    ggrid = torch.empty((N, P, 3), dtype=inp.dtype, device=inp.device)
+    ggout = torch.empty((N, Cc, P), dtype=inp.dtype, device=inp.device)
+    lib = _lib.load()
+    with torch.cuda.device(inp.device):
+        fn = getattr(lib, "sr_grid_sample3d_dbwd_" + _gs_suffix(inp))
+        check(fn(_p(ggi), _p(ggg), _p(inp), _istr(inp), _p(g), _p(go), _p(ginp), _p(ggrid),
+                 _p(ggout), N, Cc, D, H, W, P, _stream()), "grid_sample3d_dbwd")
+    return ginp, ggrid.reshape(grid.shape), ggout.reshape(grad_output.shape)
+
+
+# ------------------------------------------------------------------------------------------------
+# Fused MLP stacks
+# ------------------------------------------------------------------------------------------------
+def _pad(x, m):
+    return (x + m - 1) // m * m
+
+
+class FusedMLP:
+    """Folded (weight-norm applied, transposed, padded) copy of an MLP's parameters plus the
+    sr_mlp_desc that points at it.  `linears` is a list of dicts with keys
+    v [n,k], g [n] or None, b [n] or None, act (SR_ACT_*), skip (bool)."""
+
+    def __init__(self, d_in, multires, device):
+        self.d_in = int(d_in)
+        self.multires = int(multires)
+        self.device = torch.device(device)
+        self.bufs = []
+        self.desc = MlpDesc()
+        self._sig = None
+
+    def fold(self, linears, pe_w=None):
+        lib = _lib.load()
+        d = self.desc
+        d.n_layers = len(linears)
+        d.d_in = self.d_in
+        d.multires = self.multires
+        pw = pe_w if pe_w is not None else [1.0] * self.multires
+        for i in range(16):
+            d.pe_w[i] = float(pw[i]) if i < len(pw) else 0.0
+        if len(linears) > _lib.SR_MLP_MAX_LAYERS:
+            raise RuntimeError("FusedMLP: too many layers")
+        bufs = []
+        with torch.cuda.device(self.device):
+            for i, L in enumerate(linears):
+                v = L["v"].detach()
+                _need_cuda(v)
+                v = v.contiguous().float()
+                n, k = v.shape
+                npad, kpad = _pad(n, 128), _pad(k, 8)
+                if npad > 512 or kpad > 512:
+                    raise RuntimeError("FusedMLP: layer %dx%d exceeds the 512-wide engine" % (n, k))
+                wt = torch.empty((kpad, npad), dtype=torch.float32, device=self.device)
+                bias = torch.empty((npad,), dtype=torch.float32, device=self.device)
+                g = L.get("g")
+                b = L.get("b")
+                g = g.detach().contiguous().float().view(-1) if g is not None else None
+                b = b.detach().contiguous().float() if b is not None else None
+                check(lib.sr_fold_linear(_p(v), _p(g), _p(b), n, k, npad, kpad, _p(wt), _p(bias),
+                                         _stream()), "fold_linear")
+                bufs += [wt, bias, v, g, b]
+                ly = d.layer[i]
+                ly.wt = wt.data_ptr()
+                ly.bias = bias.data_ptr()
+                ly.k, ly.n, ly.kpad, ly.npad = k, n, kpad, npad
+                ly.act = int(L["act"])
+                ly.skip = 1 if L.get("skip") else 0
+        self.bufs = bufs  # keep device buffers alive
+        return self
+
+    def set_pe_weights(self, pe_w):
+        for i in range(16):
+            self.desc.pe_w[i] = float(pe_w[i]) if i < len(pe_w) else 0.0
+
+    def truncated_last(self, n_out):
+        """A view of the same network whose last layer only produces the first n_out outputs
+        (e.g. the SDF value without the 256-d feature): same buffers, narrower npad."""
+        t = FusedMLP(self.d_in, self.multires, self.device)
+        C.memmove(C.byref(t.desc), C.byref(self.desc), C.sizeof(MlpDesc))
+        last = t.desc.layer[t.desc.n_layers - 1]
+        full_npad = last.npad
+        npad = _pad(n_out, 128)
+        if npad != full_npad:
+            # W_T rows are npad-strided, so a narrower view needs its own copy of the columns
+            k, kpad = last.k, last.kpad
+            src = [b for b in self.bufs if b is not None and b.data_ptr() == last.wt][0]
+            bsrc = [b for b in self.bufs if b is not None and b.data_ptr() == last.bias][0]
+            wt = src[:, :npad].contiguous()
+            bias = bsrc[:npad].contiguous()
+            t.bufs = [wt, bias]
+            last.wt = wt.data_ptr()
+            last.bias = bias.data_ptr()
+            last.npad = npad
+        last.n = n_out
+        t._parent = self
+        return t
+
+
+def annealing_weights(multires, ratio):
+    """utils/utils.py:40-46 (one weight per band; the reference repeats each twice)."""
+    if ratio is None:
+        return [1.0] * multires
+    if ratio <= 0:
+        return [0.0] * multires
+    alpha = ratio * multires
+    return [(1.0 - math.cos(math.pi * min(max(alpha - float(i), 0.0), 1.0))) / 2.0
+            for i in range(multires)]
+
+
+def sdf_forward(net, pts, want_grad=False, nfeat=0):
+    _need_cuda(pts)
+    pts = pts.contiguous().float()
+    P = pts.shape[0]
+    dev = pts.device
+    sdf = torch.empty((P,), dtype=torch.float32, device=dev)
+    grad = torch.empty((P, 3), dtype=torch.float32, device=dev) if want_grad else None
+    feat = torch.empty((P, nfeat), dtype=torch.float32, device=dev) if nfeat else None
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        check(lib.sr_sdf_forward(C.byref(net.desc), _p(pts), P, _p(sdf), _p(grad), _p(feat),
+                                 int(nfeat), _stream()), "sdf_forward")
+    return sdf, grad, feat
+
+
+class LbsState:
+    """Device-side LBS inputs: channels-last weight volume + per-frame bone transforms."""
+
+    def __init__(self, ws_ncdhw, bmin, bmax, Js, parents, init_pose_inv):
+        _need_cuda(ws_ncdhw)
+        dev = ws_ncdhw.device
+        _, c, D, H, W = ws_ncdhw.shape
+        assert c == 24
+        self.D, self.H, self.W = D, H, W
+        self.device = dev
+        self.ws_cl = torch.empty((D, H, W, 24), dtype=torch.float32, device=dev)
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            check(lib.sr_lbs_weights_to_channels_last(_p(ws_ncdhw.contiguous().float()),
+                                                      _p(self.ws_cl), D, H, W, _stream()),
+                  "lbs_weights_to_channels_last")
+        self.bmin = [float(x) for x in bmin.view(-1).tolist()]
+        self.bmax = [float(x) for x in bmax.view(-1).tolist()]
+        self.Js = Js.detach().contiguous().float().view(24, 3)
+        self.parents = torch.as_tensor(parents, dtype=torch.int32, device=dev).contiguous()
+        self.ipi = init_pose_inv.detach().contiguous().float() if init_pose_inv is not None else None
+        self.A = None
+        self.trans = None
+        self.params = LbsParams()
+
+    def set_pose(self, poses, trans, want_posed_joints=False):
+        """poses [F,24,3] axis-angle, trans [F,3] -> bone transforms on device."""
+        F = poses.shape[0]
+        poses = poses.detach().contiguous().float().view(F, 24, 3)
+        self.trans = trans.detach().contiguous().float().view(F, 3)
+        self.A = torch.empty((F, 24, 4, 4), dtype=torch.float32, device=self.device)
+        pj = torch.empty((F, 24, 3), dtype=torch.float32, device=self.device) if want_posed_joints else None
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            check(lib.sr_lbs_bone_transforms(_p(poses), _p(self.Js), _p(self.parents), _p(self.ipi),
+                                             F, _p(self.A), _p(pj), _stream()), "lbs_bone_transforms")
+        p = self.params
+        p.ws_cl = self.ws_cl.data_ptr()
+        p.D, p.H, p.W = self.D, self.H, self.W
+        for i in range(3):
+            p.bmin[i] = self.bmin[i]
+            p.bmax[i] = self.bmax[i]
+        p.A = self.A.data_ptr()
+        p.trans = self.trans.data_ptr()
+        p.F = F
+        return pj
+
+
+def _lbs_ref(lbs):
+    return C.byref(lbs.params) if lbs is not None else None
+
+
+def deform_forward(net, lbs, pts, batch_inds, conds, want_jac=False, want_offset=False,
+                   want_corner_idx=False, pts_per_frame=0):
+    _need_cuda(pts)
+    pts = pts.contiguous().float().view(-1, 3)
+    P = pts.shape[0]
+    dev = pts.device
+    conds = conds.detach().contiguous().float() if conds is not None else None
+    condlen = conds.shape[-1] if conds is not None else 0
+    bi = batch_inds.contiguous().to(torch.int64) if batch_inds is not None else None
+    d = torch.empty((P, 3), dtype=torch.float32, device=dev)
+    off = torch.empty((P, 3), dtype=torch.float32, device=dev) if want_offset else None
+    jac = torch.empty((P, 3, 3), dtype=torch.float32, device=dev) if want_jac else None
+    ci = torch.empty((P, 3), dtype=torch.int32, device=dev) if want_corner_idx else None
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        check(lib.sr_deform_forward(C.byref(net.desc), _lbs_ref(lbs), _p(pts), _p(bi),
+                                    int(pts_per_frame), _p(conds), condlen, P, _p(d), _p(off),
+                                    _p(jac), _p(ci), _stream()), "deform_forward")
+    return d, off, jac, ci
+
+
+def render_forward(net, pts, normals, views, feat):
+    _need_cuda(pts, normals, views)
+    P = pts.shape[0]
+    dev = pts.device
+    nfeat = feat.shape[1] if feat is not None else 0
+    rgb = torch.empty((P, 3), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        check(lib.sr_render_forward(C.byref(net.desc), _p(pts.contiguous().float()),
+                                    _p(normals.contiguous().float()), _p(views.contiguous().float()),
+                                    _p(feat.contiguous().float() if feat is not None else None),
+                                    nfeat, P, _p(rgb), _stream()), "render_forward")
+    return rgb
+
+
+def trace_surface_points(sdf_net, def_net, lbs, cam_pos, rays, init_pts, batch_inds, conds,
+                         dthreshold=5e-5, athreshold=0.02, w1=3.05, w2=1.0, times=5):
+    """OptimizeSurfacePs (utils/FindSurfacePs.py:114-163): returns (points, converged).
+    times+1 launches are enqueued back to back; nothing syncs the host."""
+    _need_cuda(rays, init_pts)
+    dev = init_pts.device
+    P = init_pts.shape[0]
+    pts = init_pts.detach().contiguous().float().clone()
+    rays = rays.detach().contiguous().float()
+    bi = batch_inds.contiguous().to(torch.int64) if batch_inds is not None else None
+    conds = conds.detach().contiguous().float() if conds is not None else None
+    condlen = conds.shape[-1] if conds is not None else 0
+    conv = torch.zeros((P,), dtype=torch.bool, device=dev)
+    if P == 0:
+        return pts, conv
+    lists = [torch.empty((P,), dtype=torch.int32, device=dev) for _ in range(2)]
+    counters = torch.zeros((times + 3,), dtype=torch.int32, device=dev)
+    tp = TraceParams()
+    cp = [float(x) for x in cam_pos.detach().view(-1).tolist()]
+    for i in range(3):
+        tp.cam_pos[i] = cp[i]
+    tp.dthreshold, tp.athreshold, tp.w1, tp.w2 = float(dthreshold), float(athreshold), float(w1), float(w2)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        for it in range(times + 1):
+            a_in = lists[(it + 1) & 1] if it > 0 else None
+            a_out = lists[it & 1] if it < times else None
+            check(lib.sr_trace_step(C.byref(sdf_net.desc), C.byref(def_net.desc), _lbs_ref(lbs),
+                                    C.byref(tp), _p(pts), _p(rays), _p(bi), _p(conds), condlen, P,
+                                    _p(a_in), _p(a_out), _p(counters), it, _p(conv), _stream()),
+                  "trace_step")
+    return pts, conv
+
+
+def shade_geometry(sdf_net, def_net, lbs, pts, rays, batch_inds, conds, nfeat=0, want_dpos=False):
+    _need_cuda(pts, rays)
+    dev = pts.device
+    P = pts.shape[0]
+    pts = pts.detach().contiguous().float()
+    rays = rays.detach().contiguous().float()
+    bi = batch_inds.contiguous().to(torch.int64) if batch_inds is not None else None
+    conds = conds.detach().contiguous().float() if conds is not None else None
+    condlen = conds.shape[-1] if conds is not None else 0
+    normals = torch.empty((P, 3), dtype=torch.float32, device=dev)
+    crays = torch.empty((P, 3), dtype=torch.float32, device=dev)
+    feat = torch.empty((P, nfeat), dtype=torch.float32, device=dev) if nfeat else None
+    dpos = torch.empty((P, 3), dtype=torch.float32, device=dev) if want_dpos else None
+    ok = torch.empty((P,), dtype=torch.bool, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        check(lib.sr_shade_geometry(C.byref(sdf_net.desc), C.byref(def_net.desc), _lbs_ref(lbs),
+                                    _p(pts), _p(rays), _p(bi), _p(conds), condlen, P, _p(normals),
+                                    _p(crays), _p(feat), int(nfeat), _p(dpos), _p(ok), _stream()),
+              "shade_geometry")
+    return normals, crays, feat, dpos, ok
+
+
+# ------------------------------------------------------------------------------------------------
+# Seg3dLossless plumbing
+# ------------------------------------------------------------------------------------------------
+def seg3d_candidates(flag, calculated, stride_zyx):
+    """flag [D,H,W] bool, calculated [fD,fH,fW] bool -> candidate mask [D,H,W] bool."""
+    _need_cuda(flag, calculated)
+    D, H, W = flag.shape
+    fD, fH, fW = calculated.shape
+    cand = torch.empty((D, H, W), dtype=torch.bool, device=flag.device)
+    lib = _lib.load()
+    with torch.cuda.device(flag.device):
+        check(lib.sr_seg3d_candidates(_p(flag.contiguous()), _p(calculated), _p(cand), D, H, W,
+                                      int(stride_zyx[0]), int(stride_zyx[1]), int(stride_zyx[2]),
+                                      fD, fH, fW, _stream()), "seg3d_candidates")
+    return cand
