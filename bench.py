@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""Benchmark of the SelfRecon hot path on B200 (BASELINE.json metric, config[1]).
+
+One "step" = one pass of the hot path over one synthetic 512x512 frame:
+  ray part : OptimizeSurfacePs (training thresholds: dthr 5e-5, 0.5 px angle, times=10) on every
+             silhouette ray of the frame, then shading (grad f, cardinal rays, rendcond, RenderNet);
+  MC part  : discretizeSDF = coarse-to-fine 257^3 SDF grid (Seg3dLossless, ladder 33..257) + MC.
+`value` = rays/s over the ray part (whole job, all GPUs), `mc_voxels_per_sec` = 257^3 / MC part.
+Inputs are resident in HBM for `value`; `e2e` repeats the step through the reference-facing
+drop-in API with pinned host buffers, H2D/D2H inside the timed region.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+Under torchrun (N>1) every rank renders its own frame (weak scaling, no data-path collective).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F_S, F_D, F_R = 3.933184e6, 1.746944e6, 1.871872e6  # FLOP per point
+RATIO = {"sdfRatio": 1.0, "deformerRatio": 1.0, "renderRatio": 1.0}
+GRID_N = 257
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor=d["bf16_tflops"], tensor_sustained=d.get("bf16_tflops_sustained"),
+                    src="measured")
+    return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.stop = False
+        self.index = index
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop:
+            try:
+                o = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                             "--format=csv,noheader,nounits"], timeout=5).decode()
+                self.rows.append([x.strip() for x in o.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=3)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons}
+
+
+# --------------------------------------------------------------------------------------------------
+def build_scene(dev, frame_seed, H=512, W=512):
+    from selfreconcode_b200 import synth
+    sdf = synth.make_sdf().to(dev)
+    tr = synth.make_translator().to(dev)
+    sk = synth.make_skinner().to(dev)
+    rn = synth.make_render().to(dev)
+    comp = synth.CompositeDeformer([tr, sk]).to(dev)
+    poses, trans, dcond = [t.to(dev) for t in synth.make_frame_params(100 + frame_seed, 1)]
+    conds = [dcond, [poses, trans]]
+    cam = synth.camera(H, W)
+
+    def sdf_fn(p):
+        return sdf.forward_fused(p.to(dev), RATIO, False, False)[0].view(-1)
+
+    def def_fn(p, b):
+        return comp.forward_fused(p.to(dev), conds, b.to(dev), RATIO)[0]
+
+    rays = synth.make_rays(cam, 1, sdf_fn, def_fn, seed=7 + frame_seed)
+    return dict(sdf=sdf, comp=comp, rn=rn, conds=conds, cam=cam, rays=rays,
+                ang=synth.ang_threshold(cam, 0.5), synth=synth)
+
+
+def make_engine(sc, dev):
+    from selfreconcode_b200 import enable_dropin
+    enable_dropin()
+    from MCAcc import Seg3dLossless
+    sdf = sc["sdf"]
+
+    def query_func(points):
+        with torch.no_grad():
+            return sdf.forward(points.reshape(-1, 3), RATIO).reshape(1, 1, -1)
+
+    eng = Seg3dLossless(query_func=query_func, b_min=[-1.0, -1.0, -1.0], b_max=[1.0, 1.0, 1.0],
+                        resolutions=sc["synth"].MC_LADDER_257, align_corners=False, balance_value=0.0,
+                        use_cuda_impl=True).to(dev)
+    return eng
+
+
+def ray_part(sc, rays, init, bi, stats=None):
+    """trace + shade through the product ops (device tensors in / out)."""
+    from selfreconcode_b200 import ops
+    sdf, comp, rn = sc["sdf"], sc["comp"], sc["rn"]
+    tr, sk = comp.defs
+    sdf_only = sdf.fused_sdf_only()
+    sdf_only.set_pe_weights([1.0] * 6)
+    dnet = tr.fused(RATIO)
+    lbs = sk.lbs_state()
+    lbs.set_pose(sc["conds"][1][0], sc["conds"][1][1])
+    cam_pos = sc["cam"]["cam_pos"]
+    pts, conv, counters = ops.trace_surface_points(sdf_only, dnet, lbs, cam_pos, rays, init, bi, sc["conds"][0],
+                                                   5e-5, sc["ang"], 3.05, 1.0, 10, return_counters=True)
+    full = sdf.fused()
+    full.set_pe_weights([1.0] * 6)
+    n, cr, feat, _, _ = ops.shade_geometry(full, dnet, lbs, pts, rays, bi, sc["conds"][0], nfeat=256)
+    rgb = ops.render_forward(rn.fused(RATIO), pts, n, cr, feat)
+    if stats is not None:
+        stats["counters"] = counters
+    return pts, conv, rgb
+
+
+def mc_part(sc, eng):
+    import MCGpu
+    grid = eng.forward()
+    v, f = MCGpu.mc_gpu(grid[0, 0].permute(2, 1, 0).contiguous(), eng.spacing_x, eng.spacing_y, eng.spacing_z,
+                        eng.bx, eng.by, eng.bz, 0.0)
+    return grid, v, f
+
+
+def ray_part_api(sc, rays, init, bi):
+    """Same work through the reference-facing drop-in API (utils.OptimizeSurfacePs, ...)."""
+    import utils
+    sdf, comp, rn = sc["sdf"], sc["comp"], sc["rn"]
+    cam_pos = sc["cam"]["cam_pos"].to(rays.device)
+    pts, conv = utils.OptimizeSurfacePs(cam_pos, rays, init, bi, sdf, RATIO, comp, sc["conds"], dthreshold=5e-5,
+                                        athreshold=sc["ang"], w1=3.05, w2=1., times=10)
+    s, nx, feat = sdf.forward_fused(pts, RATIO, want_grad=True, want_feat=True)
+    nx = nx / nx.norm(dim=1, keepdim=True)
+    crays, dv = utils.compute_cardinal_rays(comp, pts, rays, sc["conds"], bi, RATIO, 'test')
+    with torch.no_grad():
+        rgb = utils.compute_netRender_color(rn, pts, dv, nx, crays, feat, None, RATIO)
+    return pts, conv, rgb
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_sample(n_rays, threads, seed=0, with_mc=True):
+    """The oracle (CPU port of the reference path) on a bounded sample of the same workload."""
+    from selfreconcode_b200 import synth
+    from oracle import oracle as O
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    torch.set_num_threads(threads)
+    sdf = synth.make_sdf()
+    tr = synth.make_translator()
+    sk = synth.make_skinner()
+    rn = synth.make_render()
+    poses, trans, dcond = synth.make_frame_params(100 + seed, 1)
+    sp = helpers.sdf_params(sdf)
+    tp = helpers.plain_params(tr)
+    rp = helpers.wn_params(rn)
+    A, _ = O.bone_transforms(poses, sk.Js, synth.SMPL_PARENTS, sk.init_pose)
+    lbs = dict(ws=sk.ws, bmin=sk.b_min.view(3), bmax=sk.b_max.view(3), A=A, trans=trans)
+    sdf_fn = lambda p: O.sdf_forward(sp, p, 6, 1.0)[0]
+    def_fn = lambda p, b: O.composite_deform(tp, 6, 1.0, dcond, lbs, p, b)[0]
+    cam = synth.camera(512, 512)
+    with torch.no_grad():
+        rays = synth.make_rays(cam, 1, lambda p: sdf_fn(p).view(-1), def_fn, seed=7 + seed, max_rays=n_rays)
+    bi = rays["batch_inds"]
+    t0 = time.perf_counter()
+    pts, conv, _ = O.optimize_surface_ps(cam["cam_pos"], rays["rays"], rays["init_pts"], bi, sdf_fn, def_fn,
+                                         5e-5, synth.ang_threshold(cam, 0.5), 3.05, 1.0, 10)
+    s, g, feat = O.sdf_value_and_grad(sp, pts, 6, 1.0)
+    nx = g / g.norm(dim=1, keepdim=True)
+    cr, ds, J, ok = O.cardinal_rays(lambda p: def_fn(p, bi), pts, rays["rays"])
+    with torch.no_grad():
+        O.render_forward(rp, pts, nx, cr, feat, 4, 1.0)
+    t_ray = time.perf_counter() - t0
+    out = {"rays": int(pts.shape[0]), "ray_seconds": t_ray, "rays_per_sec": pts.shape[0] / t_ray}
+    if with_mc:
+        from oracle import c_api
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            grid, calc = O.seg3d_forward(lambda q: sdf_fn(q).view(-1), [-1.0] * 3, [1.0] * 3,
+                                         synth.MC_LADDER_65, 0.0)
+        spc, org = O.mc_world_params([-1.0] * 3, [1.0] * 3, (65, 65, 65))
+        c_api.marching_cubes(grid.permute(2, 1, 0).contiguous().numpy(), helpers.mc_tri_table(), 0.0, spc, org)
+        t_mc = time.perf_counter() - t0
+        out.update({"mc_grid": 65, "mc_seconds": t_mc, "mc_voxels_per_sec": 65 ** 3 / t_mc,
+                    "mc_queried": int(calc.sum())})
+    return out
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle port) on host cores, bounded sample."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = 192
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_reference_sample(32, threads, with_mc=False)
+    vals, ts = [], []
+    for _ in range(args.steps):
+        r = cpu_reference_sample(n, threads, with_mc=False)
+        vals.append(r["rays_per_sec"])
+        ts.append(r["ray_seconds"])
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": "rays_per_sec", "value": v, "unit": "rays/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(ts)),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config[1]: 512x512 synthetic frame, 8x512 SDF + Deformer(LBS) + RenderNet; "
+                                   "bounded sample of %d rays per step on host cores" % n},
+            "cpu_baseline": {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
+                             "sample": "%d rays of the frame: OptimizeSurfacePs(times=10)+shading through oracle/oracle.py" % n},
+            "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    assert torch.cuda.is_available(), "bench.py needs a GPU (the product has no CPU path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+    from selfreconcode_b200 import _lib, ops
+    _lib.load()
+    sc = build_scene(dev, frame_seed=rank)
+    eng = make_engine(sc, dev)
+    R = sc["rays"]
+    n_rays = R["rays"].shape[0]
+    rays_d, init_d, bi_d = R["rays"].to(dev), R["init_pts"].to(dev), R["batch_inds"].to(dev)
+    rays_h, init_h, bi_h = R["rays"].pin_memory(), R["init_pts"].pin_memory(), R["batch_inds"].pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for _ in range(max(args.warmup, 3)):
+        ray_part(sc, rays_d, init_d, bi_d)
+        mc_part(sc, eng)
+    torch.cuda.synchronize()
+    ops.LAUNCHES = 0
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    ray_ms, mc_ms, trace_ms = [], [], []
+    stats = {}
+    barrier()
+    with ClockSampler(local) as clk:
+        t_wall0 = time.perf_counter()
+        for _ in range(args.steps):
+            flush.zero_()
+            e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+            e0.record()
+            ray_part(sc, rays_d, init_d, bi_d, stats)
+            e1.record()
+            flush.zero_()
+            e2.record()
+            grid, v, f = mc_part(sc, eng)
+            e3.record()
+            torch.cuda.synchronize()
+            ray_ms.append(e0.elapsed_time(e1))
+            mc_ms.append(e2.elapsed_time(e3))
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    launches = ops.LAUNCHES
+    # per-kernel timing of the dominant kernel (trace_kernel): events around the 11 launches
+    tk = []
+    for _ in range(3):
+        flush.zero_()
+        a, b = ev(), ev()
+        sdf_only = sc["sdf"].fused_sdf_only()
+        dnet = sc["comp"].defs[0].fused(RATIO)
+        lbs = sc["comp"].defs[1].lbs_state()
+        a.record()
+        _, _, counters = ops.trace_surface_points(sdf_only, dnet, lbs, sc["cam"]["cam_pos"], rays_d, init_d, bi_d,
+                                                  sc["conds"][0], 5e-5, sc["ang"], 3.05, 1.0, 10,
+                                                  return_counters=True)
+        b.record()
+        torch.cuda.synchronize()
+        tk.append(a.elapsed_time(b))
+    cnt = counters.cpu().tolist()
+    ray_iters = sum(cnt[1:11])
+    trace_flops = (n_rays + 3.0 * ray_iters) * (F_S + F_D)  # algorithmic: (1+3k) per ray
+    # MC sweep kernels alone (classify + scan + emit) on the last grid
+    sd = grid[0, 0].permute(2, 1, 0).contiguous()
+    mk = []
+    for _ in range(5):
+        flush.zero_()
+        a, b = ev(), ev()
+        a.record()
+        vv, ff = ops.marching_cubes(sd, 1, 1, 1, 0, 0, 0, 0.0)
+        b.record()
+        torch.cuda.synchronize()
+        mk.append(a.elapsed_time(b))
+    mc_bytes = 4.0 * GRID_N ** 3 + 12.0 * vv.shape[0] + 24.0 * ff.shape[0]
+
+    # ---- e2e: host buffers in, results out, through the drop-in API
+    e2e_ms = []
+    for i in range(args.steps + 1):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r_d = rays_h.to(dev, non_blocking=True)
+        i_d = init_h.to(dev, non_blocking=True)
+        b_d = bi_h.to(dev, non_blocking=True)
+        pts, conv, rgb = ray_part_api(sc, r_d, i_d, b_d)
+        rgb_h = rgb.cpu()
+        conv_h = conv.cpu()
+        torch.cuda.synchronize()
+        if i > 0:
+            e2e_ms.append(1e3 * (time.perf_counter() - t0))
+    h2d = rays_h.numel() * 4 + init_h.numel() * 4 + bi_h.numel() * 8
+    d2h = rgb_h.numel() * 4 + conv_h.numel()
+
+    t_ray = torch.tensor([float(np.mean(ray_ms)), float(np.mean(mc_ms)), float(np.mean(e2e_ms)),
+                          float(n_rays)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        mx = t_ray.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t_ray.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ray_t, mc_t, e2e_t, total_rays = mx[0].item(), mx[1].item(), mx[2].item(), sm[3].item()
+    else:
+        ray_t, mc_t, e2e_t, total_rays = t_ray[0].item(), t_ray[1].item(), t_ray[2].item(), float(n_rays)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    trace_s = float(np.mean(tk)) * 1e-3
+    mc_s = float(np.mean(mk)) * 1e-3
+    line = {
+        "metric": "rays_per_sec", "value": total_rays / (ray_t * 1e-3), "unit": "rays/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ray_t + mc_t, "ms_ray_part": ray_t, "ms_mc_part": mc_t,
+        "mc_voxels_per_sec": world * GRID_N ** 3 / (mc_t * 1e-3),
+        "mc_queried_voxels": int(eng.last_num_queried), "mc_vertices": int(v.shape[0]), "mc_faces": int(f.shape[0]),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config[1]: one 512x512 synthetic frame per GPU, %d silhouette rays, 8x512 SDF + "
+                               "Deformer(MLP+LBS 129x225x65) + RenderNet; trace times=10 dthr=5e-5; 257^3 "
+                               "coarse-to-fine grid + MC" % n_rays,
+                   "rays_per_frame": n_rays, "mc_grid": GRID_N, "l2": "256 MiB flush between timed regions",
+                   "parallelism": "frames sharded, dp%d, no data-path collective" % world},
+        "e2e": {"value": total_rays / (e2e_t * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms": e2e_t},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "trace_kernel (11 launches per trace)", "bound": "tensor",
+                     "achieved": trace_flops / trace_s / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s",
+                     "frac": trace_flops / trace_s / 1e12 / pk["tensor"], "traffic": None,
+                     "peak_source": pk["src"] + " bf16 cuBLAS burst",
+                     "note": "fp32 FFMA engine (no tensor cores yet): fp32 FFMA peak is ~72 TFLOP/s; "
+                             "algorithmic FLOPs = (rays + 3*ray_iterations) * 5.680 MFLOP",
+                     "ms": trace_s * 1e3, "ray_iterations": int(ray_iters)},
+        "roofline_mc": {"kernel": "mc_classify+mc_scan+mc_emit", "bound": "hbm",
+                        "achieved": mc_bytes / mc_s / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                        "frac": mc_bytes / mc_s / 1e9 / pk["hbm"], "traffic": None, "ms": mc_s * 1e3,
+                        "peak_source": pk["src"]},
+        "clocks": clk.summary(),
+        "wall_s_timed_region": t_wall,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        cb = cpu_reference_sample(192, threads, with_mc=True)
+        line["cpu_baseline"] = {"value": cb["rays_per_sec"], "unit": "rays/s", "cores": threads, "kind": "port",
+                                "sample": "192 rays of the same frame (trace times=10 + shading) and a 65^3 "
+                                          "coarse-to-fine grid + MC through oracle/ (torch fp32 CPU + C)",
+                                "mc_voxels_per_sec": cb.get("mc_voxels_per_sec"), "mc_grid": cb.get("mc_grid"),
+                                "ray_seconds": cb["ray_seconds"], "mc_seconds": cb.get("mc_seconds")}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -11,11 +11,24 @@ import math
 import torch
 
 from . import _lib
-from ._lib import MlpDesc, LbsParams, TraceParams, check
+from ._lib import MlpDesc, LbsParams, TraceParams
+from ._lib import check as _check
+
+
+LAUNCHES = 0  # kernels launched by this module since it was last reset (bench.py reads it)
+
+_KERNELS_PER_CALL = {"mc_count": 2}
 
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def check(code, what):
+    """C-ABI return code -> RuntimeError; also counts the kernels the call launched."""
+    global LAUNCHES
+    _check(code, what)
+    LAUNCHES += _KERNELS_PER_CALL.get(what, 1)
 
 
 def _p(t):
@@ -408,7 +421,8 @@ def render_forward(net, pts, normals, views, feat):
 
 
 def trace_surface_points(sdf_net, def_net, lbs, cam_pos, rays, init_pts, batch_inds, conds,
-                         dthreshold=5e-5, athreshold=0.02, w1=3.05, w2=1.0, times=5):
+                         dthreshold=5e-5, athreshold=0.02, w1=3.05, w2=1.0, times=5,
+                         return_counters=False):
     """OptimizeSurfacePs (utils/FindSurfacePs.py:114-163): returns (points, converged).
     times+1 launches are enqueued back to back; nothing syncs the host."""
     _need_cuda(rays, init_pts)
@@ -421,7 +435,8 @@ def trace_surface_points(sdf_net, def_net, lbs, cam_pos, rays, init_pts, batch_i
     condlen = conds.shape[-1] if conds is not None else 0
     conv = torch.zeros((P,), dtype=torch.bool, device=dev)
     if P == 0:
-        return pts, conv
+        return (pts, conv, torch.zeros((times + 3,), dtype=torch.int32, device=dev)) if return_counters \
+            else (pts, conv)
     lists = [torch.empty((P,), dtype=torch.int32, device=dev) for _ in range(2)]
     counters = torch.zeros((times + 3,), dtype=torch.int32, device=dev)
     tp = TraceParams()
@@ -438,6 +453,8 @@ def trace_surface_points(sdf_net, def_net, lbs, cam_pos, rays, init_pts, batch_i
                                     C.byref(tp), _p(pts), _p(rays), _p(bi), _p(conds), condlen, P,
                                     _p(a_in), _p(a_out), _p(counters), it, _p(conv), _stream()),
                   "trace_step")
+    if return_counters:  # counters[it] = rays updated in iteration it (it = 1..times)
+        return pts, conv, counters
     return pts, conv
 
 

@@ -164,13 +164,13 @@ def make_rays(cam, n_frames, sdf_fn, deform_fn, seed=7, jitter=5e-3, radius=0.6,
     sdf_fn(points [P,3]) -> [P];  deform_fn(points [P,3], batch_inds [P]) -> [P,3]; both may run
     on any device (CPU tensors in, any device out)."""
     rows, cols, pts = sphere_pixels(cam, radius)
-    pts = project_to_surface(sdf_fn, pts / pts.norm(dim=1, keepdim=True))
     n = pts.shape[0]
     g = torch.Generator().manual_seed(seed)
     if max_rays is not None and n > max_rays:
         sel = torch.randperm(n, generator=g)[:max_rays].sort()[0]
         rows, cols, pts = rows[sel], cols[sel], pts[sel]
         n = max_rays
+    pts = project_to_surface(sdf_fn, pts / pts.norm(dim=1, keepdim=True))
     batch = torch.arange(n_frames).view(-1, 1).expand(n_frames, n).reshape(-1)
     pstar = pts.repeat(n_frames, 1)
     rows_all = rows.repeat(n_frames)
