@@ -64,13 +64,15 @@ int sr_minv3x3_bwd_f64(const double* grads, const double* invs, double* outs, in
  *                 int64 (winding reversed like d_conver_ijkd_to_pindex) in CANONICAL order:
  *                 vertices sorted by owning edge key (i,j,k,dir), faces by (voxel, tri#).
  *                 Corners that reference a never-created boundary-layer vertex get -1,
- *                 as in the reference.
+ *                 as in the reference.  `i_offset` (0 for a whole grid) is added to the x
+ *                 voxel index before scaling, so an x-slab of a larger grid produces the
+ *                 same bits as the whole-grid call (multi-GPU extraction).
  * ------------------------------------------------------------------------------------------ */
 int64_t sr_mc_work_bytes(int nx, int ny, int nz);
 int sr_mc_count(const float* sdf, int nx, int ny, int nz, float iso, void* work, int32_t* counts,
                 cudaStream_t s);
 int sr_mc_emit(const float* sdf, int nx, int ny, int nz, float iso, float xstep, float ystep,
-               float zstep, float xmin, float ymin, float zmin, const void* work,
+               float zstep, float xmin, float ymin, float zmin, int i_offset, const void* work,
                float* vertices, int64_t vcap, int64_t* faces, int64_t fcap, cudaStream_t s);
 
 /* ------------------------------------------------------------------------------------------

@@ -37,7 +37,7 @@ def minv3x3_bwd(grads, invs):
     return out
 
 
-def marching_cubes(sdf, tri_table, iso=0.0, step=(1., 1., 1.), origin=(0., 0., 0.)):
+def marching_cubes(sdf, tri_table, iso=0.0, step=(1., 1., 1.), origin=(0., 0., 0.), i_offset=0):
     """sdf [nx,ny,nz] f32; tri_table int32 [256,16].  -> verts [V,3] f32, faces [F,3] i64 (canonical)."""
     sdf = np.ascontiguousarray(sdf, dtype=np.float32)
     tt = np.ascontiguousarray(tri_table, dtype=np.int32)
@@ -47,7 +47,8 @@ def marching_cubes(sdf, tri_table, iso=0.0, step=(1., 1., 1.), origin=(0., 0., 0
     f.restype = C.c_int
     args = lambda v, fc: (_ptr(sdf), C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_float(iso), _ptr(tt),
                           C.c_float(step[0]), C.c_float(step[1]), C.c_float(step[2]),
-                          C.c_float(origin[0]), C.c_float(origin[1]), C.c_float(origin[2]), v, fc,
+                          C.c_float(origin[0]), C.c_float(origin[1]), C.c_float(origin[2]), C.c_int(i_offset),
+                          v, fc,
                           _ptr(counts))
     assert f(*args(C.c_void_p(0), C.c_void_p(0))) == 0
     verts = np.empty((int(counts[0]), 3), dtype=np.float32)

@@ -89,8 +89,8 @@ static const int kOwner[12][4] = {{0, 0, 0, 0}, {1, 0, 0, 1}, {0, 1, 0, 0}, {0, 
 
 /* Returns 0 on success. counts[0]=V, counts[1]=F.  If verts/faces are NULL only counts. */
 int orc_marching_cubes(const float* sdf, int nx, int ny, int nz, float iso, const int* tri_table,
-                       float xs, float ys, float zs, float x0, float y0, float z0, float* verts,
-                       int64_t* faces, int64_t* counts) {
+                       float xs, float ys, float zs, float x0, float y0, float z0, int i_offset,
+                       float* verts, int64_t* faces, int64_t* counts) {
   const int64_t nvox = (int64_t)nx * ny * nz;
   int32_t* vid = (int32_t*)malloc(sizeof(int32_t) * nvox * 3);
   if (!vid) return 1;
@@ -115,8 +115,8 @@ int orc_marching_cubes(const float* sdf, int nx, int ny, int nz, float iso, cons
           if (((idx >> a) & 1) == ((idx >> b) & 1)) continue;
           const float t = orc_get_offset(v[a], v[b], iso);
           if (verts) {
-            float px = (float)i, py = (float)j, pz = (float)k;
-            if (e == 0) px = (float)i + (0.0f + t);
+            float px = (float)(i + i_offset), py = (float)j, pz = (float)k;
+            if (e == 0) px = (float)(i + i_offset) + (0.0f + t);
             if (e == 3) py = (float)j + (1.0f - t); /* corner 3 -> corner 0, direction -y */
             if (e == 8) pz = (float)k + (0.0f + t);
             verts[3 * V + 0] = fmaf(px, xs, x0); /* d_scale_vertices: FMA-contracted */

@@ -53,7 +53,7 @@ SIGNATURES = {
     "sr_minv3x3_bwd_f64": (C.c_int, [c_f, c_f, c_f, i64, stream_t]),
     "sr_mc_work_bytes": (i64, [i32, i32, i32]),
     "sr_mc_count": (C.c_int, [c_f, i32, i32, i32, f32, c_f, c_f, stream_t]),
-    "sr_mc_emit": (C.c_int, [c_f, i32, i32, i32, f32, f32, f32, f32, f32, f32, f32, c_f, c_f, i64,
+    "sr_mc_emit": (C.c_int, [c_f, i32, i32, i32, f32, f32, f32, f32, f32, f32, f32, i32, c_f, c_f, i64,
                              c_f, i64, stream_t]),
     "sr_interp2x3d_fwd_f32": (C.c_int, [c_f, c_f, c_f, i32, i32, i32, i32, f32, stream_t]),
     "sr_interp2x3d_bwd_f32": (C.c_int, [c_f, c_f, i32, i32, i32, i32, stream_t]),

@@ -310,8 +310,8 @@ __device__ __forceinline__ long long vertex_id(const McLayout& L, int oi, int oj
 
 __global__ void __launch_bounds__(kThreads)
 mc_emit_kernel(const float* __restrict__ sdf, McLayout L, float iso, float xs, float ys, float zs,
-               float x0, float y0, float z0, float* __restrict__ verts, long long vcap,
-               long long* __restrict__ faces, long long fcap) {
+               float x0, float y0, float z0, int i_offset, float* __restrict__ verts,
+               long long vcap, long long* __restrict__ faces, long long fcap) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long word0 = (long long)blockIdx.x * kWordsPerCta + (long long)warp * kWordsPerWarp;
   const uint32_t cta_v = L.cta_v[blockIdx.x], cta_t = L.cta_t[blockIdx.x];
@@ -344,7 +344,7 @@ mc_emit_kernel(const float* __restrict__ sdf, McLayout L, float iso, float xs, f
     const uint32_t bitm = 1u << lane, lt = bitm - 1u;
     if ((fx | fy | fz) & bitm) {
       long long vid = (long long)vbase + __popc(fx & lt) + __popc(fy & lt) + __popc(fz & lt);
-      const float fi = (float)i, fj = (float)j, fk = (float)k;
+      const float fi = (float)(i + i_offset), fj = (float)j, fk = (float)k;
       if (fx & bitm) {
         const float t = edge_offset(v[0], v[1], iso);
         if (vid < vcap) {
@@ -424,14 +424,14 @@ int sr_mc_count(const float* sdf, int nx, int ny, int nz, float iso, void* work,
 }
 
 int sr_mc_emit(const float* sdf, int nx, int ny, int nz, float iso, float xstep, float ystep,
-               float zstep, float xmin, float ymin, float zmin, const void* work, float* vertices,
-               int64_t vcap, int64_t* faces, int64_t fcap, cudaStream_t s) {
+               float zstep, float xmin, float ymin, float zmin, int i_offset, const void* work,
+               float* vertices, int64_t vcap, int64_t* faces, int64_t fcap, cudaStream_t s) {
   if (nx <= 0 || ny <= 0 || nz <= 0 || !sdf || !work) return SR_EINVAL;
   if ((vcap > 0 && !vertices) || (fcap > 0 && !faces)) return SR_EINVAL;
   if (vcap == 0 && fcap == 0) return SR_OK;
   McLayout L = make_layout(nx, ny, nz, const_cast<void*>(work));
   mc_emit_kernel<<<L.nctas, kThreads, 0, s>>>(sdf, L, iso, xstep, ystep, zstep, xmin, ymin, zmin,
-                                               vertices, (long long)vcap, (long long*)faces,
+                                               i_offset, vertices, (long long)vcap, (long long*)faces,
                                                (long long)fcap);
   return sr_launch_status();
 }

@@ -73,7 +73,8 @@ def minv3x3_backward(grads, invs):
 _mc_work = {}
 
 
-def marching_cubes(sdfs, xstep=1.0, ystep=1.0, zstep=1.0, xmin=0.0, ymin=0.0, zmin=0.0, iso=0.0):
+def marching_cubes(sdfs, xstep=1.0, ystep=1.0, zstep=1.0, xmin=0.0, ymin=0.0, zmin=0.0, iso=0.0,
+                   i_offset=0):
     """sdfs [NX,NY,NZ] f32 contiguous CUDA -> (vertices [V,3] f32, faces [F,3] i64), canonical
     (deterministic) order.  One device->host read of the two counters, like the reference."""
     _need_cuda(sdfs)
@@ -95,7 +96,8 @@ def marching_cubes(sdfs, xstep=1.0, ystep=1.0, zstep=1.0, xmin=0.0, ymin=0.0, zm
         faces = torch.empty((nf, 3), dtype=torch.int64, device=dev)
         if nv or nf:
             check(lib.sr_mc_emit(_p(sdfs), nx, ny, nz, float(iso), float(xstep), float(ystep),
-                                 float(zstep), float(xmin), float(ymin), float(zmin), _p(work),
+                                 float(zstep), float(xmin), float(ymin), float(zmin), int(i_offset),
+                                 _p(work),
                                  _p(verts), nv, _p(faces), nf, _stream()), "mc_emit")
     return verts, faces
 
