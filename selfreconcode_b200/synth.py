@@ -171,7 +171,7 @@ def make_rays(cam, n_frames, sdf_fn, deform_fn, seed=7, jitter=5e-3, radius=0.6,
         rows, cols, pts = rows[sel], cols[sel], pts[sel]
         n = max_rays
     pts = project_to_surface(sdf_fn, pts / pts.norm(dim=1, keepdim=True))
-    batch = torch.arange(n_frames).view(-1, 1).expand(n_frames, n).reshape(-1)
+    batch = torch.arange(n_frames).view(-1, 1).expand(n_frames, n).reshape(-1).clone()
     pstar = pts.repeat(n_frames, 1)
     rows_all = rows.repeat(n_frames)
     cols_all = cols.repeat(n_frames)
