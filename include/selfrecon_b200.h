@@ -148,6 +148,8 @@ typedef struct sr_mlp_layer {
   int npad;          /* multiple of 128, <= 512 */
   int act;           /* SR_ACT_* applied to this layer's output */
   int skip;          /* 1: input = cat([x, net_input]) / sqrt(2) (network.py:88-89) */
+  const float* wb;   /* [pad8(n)][pad128(k)] device: un-transposed padded copy streamed by the
+                        reverse-mode pass (may be NULL when only forward kernels are used) */
 } sr_mlp_layer;
 
 typedef struct sr_mlp_desc {
@@ -162,7 +164,8 @@ typedef struct sr_mlp_desc {
  *   v: [n,k] row-major (torch nn.Linear.weight), g: [n] or NULL, b: [n] or NULL.
  *   wt: [kpad][npad], bias_out: [npad].  (network.py:65-66, RenderNet.py:46-47) */
 int sr_fold_linear(const float* v, const float* g, const float* b, int n, int k, int npad,
-                   int kpad, float* wt, float* bias_out, cudaStream_t s);
+                   int kpad, float* wt, float* bias_out, float* wb /* [pad8(n)][pad128(k)] or NULL */,
+                   cudaStream_t s);
 
 /* SDF network.  pts [P,3] -> sdf[P]; optional grad[P,3] (= d sdf / d pts, forward-mode),
  * optional feat[P,nfeat] (outputs 1..nfeat of the last layer = `rendcond`).            */
@@ -214,7 +217,8 @@ int sr_render_forward(const sr_mlp_desc* net, const float* pts, const float* nor
  * sr_trace_init evaluates the initial test and builds the first active list;
  * sr_trace_iter performs ONE damped-Newton iteration on the active list (update + re-test)
  * and writes the next list.  The host launches it `times` times back to back -- no host
- * sync; an empty list makes the launch a no-op.
+ * sync; an empty list makes the launch a no-op.  dnet == NULL means the identity deformer
+ * D(p) = p (then lbs must be NULL too).
  * ------------------------------------------------------------------------------------------ */
 typedef struct sr_trace_params {
   float cam_pos[3];
@@ -228,6 +232,19 @@ int sr_trace_step(const sr_mlp_desc* sdf, const sr_mlp_desc* dnet, const sr_lbs_
                   const int64_t* batch_inds, const float* conds, int condlen, int64_t P,
                   const int32_t* active_in, int32_t* active_out, int32_t* counters, int iter,
                   uint8_t* converged, cudaStream_t s);
+
+/* Reverse-mode variant of sr_trace_step (same contract, same results up to rounding): the
+ * gradient of the scalar loss is obtained with one forward + one backward sweep per network
+ * (2 x (F_s+F_d) per ray-iteration instead of the 4 x of forward-mode tangents), which is what
+ * the reference's autograd.grad does (FindSurfacePs.py:148).  `scratch` holds act'(z) of the
+ * hidden layers between the two sweeps: sr_trace_scratch_bytes() bytes, caller allocated.
+ * Requires every layer's `wb`. */
+int64_t sr_trace_scratch_bytes(void);
+int sr_trace_step_rev(const sr_mlp_desc* sdf, const sr_mlp_desc* dnet, const sr_lbs_params* lbs,
+                      const sr_trace_params* tp, float* pts, const float* rays,
+                      const int64_t* batch_inds, const float* conds, int condlen, int64_t P,
+                      const int32_t* active_in, int32_t* active_out, int32_t* counters, int iter,
+                      uint8_t* converged, float* scratch, cudaStream_t s);
 
 /* Geometry part of shading at converged points (infer path, model/network.py:356-361;
  * utils/utils.py:155-169): n = normalize(grad f), cardinal ray = normalize(J^-1 v)

@@ -24,7 +24,8 @@ stream_t = C.c_void_p
 
 class MlpLayer(C.Structure):
     _fields_ = [("wt", C.c_void_p), ("bias", C.c_void_p), ("k", C.c_int), ("n", C.c_int),
-                ("kpad", C.c_int), ("npad", C.c_int), ("act", C.c_int), ("skip", C.c_int)]
+                ("kpad", C.c_int), ("npad", C.c_int), ("act", C.c_int), ("skip", C.c_int),
+                ("wb", C.c_void_p)]
 
 
 class MlpDesc(C.Structure):
@@ -71,7 +72,7 @@ SIGNATURES = {
                                            i32, i32, i64, stream_t]),
     "sr_grid_sample3d_dbwd_f64": (C.c_int, [c_f, c_f, c_f, C.POINTER(i64), c_f, c_f, c_f, c_f, c_f,
                                             i32, i32, i32, i32, i32, i64, stream_t]),
-    "sr_fold_linear": (C.c_int, [c_f, c_f, c_f, i32, i32, i32, i32, c_f, c_f, stream_t]),
+    "sr_fold_linear": (C.c_int, [c_f, c_f, c_f, i32, i32, i32, i32, c_f, c_f, c_f, stream_t]),
     "sr_sdf_forward": (C.c_int, [C.POINTER(MlpDesc), c_f, i64, c_f, c_f, c_f, i32, stream_t]),
     "sr_lbs_bone_transforms": (C.c_int, [c_f, c_f, c_f, c_f, i32, c_f, c_f, stream_t]),
     "sr_lbs_weights_to_channels_last": (C.c_int, [c_f, c_f, i32, i32, i32, stream_t]),
@@ -82,6 +83,10 @@ SIGNATURES = {
     "sr_trace_step": (C.c_int, [C.POINTER(MlpDesc), C.POINTER(MlpDesc), C.POINTER(LbsParams),
                                 C.POINTER(TraceParams), c_f, c_f, c_f, c_f, i32, i64, c_f, c_f,
                                 c_f, i32, c_f, stream_t]),
+    "sr_trace_scratch_bytes": (i64, []),
+    "sr_trace_step_rev": (C.c_int, [C.POINTER(MlpDesc), C.POINTER(MlpDesc), C.POINTER(LbsParams),
+                                    C.POINTER(TraceParams), c_f, c_f, c_f, c_f, i32, i64, c_f, c_f,
+                                    c_f, i32, c_f, c_f, stream_t]),
     "sr_shade_geometry": (C.c_int, [C.POINTER(MlpDesc), C.POINTER(MlpDesc), C.POINTER(LbsParams),
                                     c_f, c_f, c_f, c_f, i32, i64, c_f, c_f, c_f, i32, c_f, c_f,
                                     stream_t]),

@@ -149,37 +149,58 @@ __device__ __forceinline__ int tri_count(uint64_t packed) {
   return (16 - nf) / 3;
 }
 
-// Loads the 8 corner values of voxel (i,j,k) (k = 32*kw + lane) and returns the cube index.
-// Corner numbering, (x,y,z)=(i,j,k) offsets: c0 000, c1 100, c2 110, c3 010, c4 001, c5 101,
-// c6 111, c7 011.  Returns -1 for lanes that are not valid cells.
-__device__ __forceinline__ int load_cube(const float* __restrict__ sdf, int nx, int ny, int nz,
-                                         int i, int j, int k, float iso, float v[8]) {
-  const bool cell = (i < nx - 1) && (j < ny - 1) && (k < nz - 1);
-  // rows: r0=(i,j) r1=(i+1,j) r2=(i+1,j+1) r3=(i,j+1); indices clamped so every lane can
-  // take part in the shuffles below.
+// Raw loads for the voxels (i,j,32*kw+lane): the four z-rows r0=(i,j) r1=(i+1,j) r2=(i+1,j+1)
+// r3=(i,j+1) at k, plus (lane 31 only) at k+1.  Indices are clamped so every lane loads something
+// and can take part in the shuffles of cube_index().  Split from the index computation so the
+// classify loop can issue the loads of word n+1 before it ballots word n (memory-level
+// parallelism: the first version had ~4 loads in flight per warp and ran at 5 % of HBM).
+struct CubeLoads {
+  float a[4];
+  float b[4];  // valid in lane 31 only
+};
+__device__ __forceinline__ CubeLoads cube_loads(const float* __restrict__ sdf, int nx, int ny,
+                                                int nz, int i, int j, int k) {
   const int i1 = min(i + 1, nx - 1), j1 = min(j + 1, ny - 1);
+  const int ic = min(i, nx - 1);
   const int kc = min(k, nz - 1);
   const long long snz = nz;
-  const float* r0 = sdf + ((long long)i * ny + j) * snz;
+  const float* r0 = sdf + ((long long)ic * ny + j) * snz;
   const float* r1 = sdf + ((long long)i1 * ny + j) * snz;
   const float* r2 = sdf + ((long long)i1 * ny + j1) * snz;
-  const float* r3 = sdf + ((long long)i * ny + j1) * snz;
-  float a0 = __ldg(r0 + kc), a1 = __ldg(r1 + kc), a2 = __ldg(r2 + kc), a3 = __ldg(r3 + kc);
-  // value at k+1: neighbour lane, except lane 31 which loads it.
-  float b0 = __shfl_down_sync(0xffffffffu, a0, 1);
-  float b1 = __shfl_down_sync(0xffffffffu, a1, 1);
-  float b2 = __shfl_down_sync(0xffffffffu, a2, 1);
-  float b3 = __shfl_down_sync(0xffffffffu, a3, 1);
+  const float* r3 = sdf + ((long long)ic * ny + j1) * snz;
+  CubeLoads c;
+  c.a[0] = __ldg(r0 + kc); c.a[1] = __ldg(r1 + kc); c.a[2] = __ldg(r2 + kc); c.a[3] = __ldg(r3 + kc);
+  c.b[0] = c.b[1] = c.b[2] = c.b[3] = 0.f;
   if ((threadIdx.x & 31) == 31) {
     const int k1 = min(k + 1, nz - 1);
-    b0 = __ldg(r0 + k1); b1 = __ldg(r1 + k1); b2 = __ldg(r2 + k1); b3 = __ldg(r3 + k1);
+    c.b[0] = __ldg(r0 + k1); c.b[1] = __ldg(r1 + k1); c.b[2] = __ldg(r2 + k1); c.b[3] = __ldg(r3 + k1);
   }
-  v[0] = a0; v[1] = a1; v[2] = a2; v[3] = a3; v[4] = b0; v[5] = b1; v[6] = b2; v[7] = b3;
+  return c;
+}
+
+// Corner numbering, (x,y,z)=(i,j,k) offsets: c0 000, c1 100, c2 110, c3 010, c4 001, c5 101,
+// c6 111, c7 011.  Returns the cube index, or -1 for lanes that are not valid cells.
+__device__ __forceinline__ int cube_index(const CubeLoads& c, int nx, int ny, int nz, int i, int j,
+                                          int k, float iso, float v[8]) {
+  const bool cell = (i < nx - 1) && (j < ny - 1) && (k < nz - 1);
+  const bool last = (threadIdx.x & 31) == 31;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float up = __shfl_down_sync(0xffffffffu, c.a[r], 1);  // value at k+1 from the neighbour lane
+    v[r] = c.a[r];
+    v[4 + r] = last ? c.b[r] : up;
+  }
   if (!cell) return -1;
   int idx = 0;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) idx |= (v[c] < iso) ? (1 << c) : 0;
+  for (int q = 0; q < 8; ++q) idx |= (v[q] < iso) ? (1 << q) : 0;
   return idx;
+}
+
+__device__ __forceinline__ int load_cube(const float* __restrict__ sdf, int nx, int ny, int nz,
+                                         int i, int j, int k, float iso, float v[8]) {
+  const CubeLoads c = cube_loads(sdf, nx, ny, nz, i, j, k);
+  return cube_index(c, nx, ny, nz, i, j, k, iso, v);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -188,17 +209,26 @@ mc_classify_kernel(const float* __restrict__ sdf, McLayout L, float iso) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long word0 = (long long)blockIdx.x * kWordsPerCta + (long long)warp * kWordsPerWarp;
   uint32_t my_nv = 0, my_nt = 0;  // lane `it` keeps the counts of word0+it
+  // (i, j, kw) of the warp's first word, then advanced incrementally: the per-word 64-bit
+  // div/mod of the first version made the kernel issue-bound (ncu: SM 72 %, DRAM 5 %).
+  int kw = (int)((uint32_t)word0 % (uint32_t)L.nwz);
+  uint32_t ij0 = (uint32_t)word0 / (uint32_t)L.nwz;
+  int j = (int)(ij0 % (uint32_t)L.ny), i = (int)(ij0 / (uint32_t)L.ny);
+  CubeLoads cur = cube_loads(sdf, L.nx, L.ny, L.nz, min(i, L.nx - 1), j, kw * 32 + lane);
   for (int it = 0; it < kWordsPerWarp; ++it) {
     const long long word = word0 + it;
+    // coordinates of the next word + its loads, issued before this word is reduced
+    int nkw = kw + 1, nj = j, ni = i;
+    if (nkw == L.nwz) { nkw = 0; if (++nj == L.ny) { nj = 0; ++ni; } }
+    CubeLoads nxt = cur;
+    if (it + 1 < kWordsPerWarp && word + 1 < L.nwords)
+      nxt = cube_loads(sdf, L.nx, L.ny, L.nz, ni, nj, nkw * 32 + lane);
     uint32_t fx = 0, fy = 0, fz = 0;
     int nt = 0;
     if (word < L.nwords) {  // warp-uniform
-      const int kw = (int)(word % L.nwz);
-      const long long ij = word / L.nwz;
-      const int j = (int)(ij % L.ny), i = (int)(ij / L.ny);
       const int k = kw * 32 + lane;
       float v[8];
-      const int idx = load_cube(sdf, L.nx, L.ny, L.nz, i, j, k, iso, v);
+      const int idx = cube_index(cur, L.nx, L.ny, L.nz, i, j, k, iso, v);
       bool ex = false, ey = false, ez = false;
       int t = 0;
       if (idx > 0 && idx < 255) {
@@ -210,7 +240,9 @@ mc_classify_kernel(const float* __restrict__ sdf, McLayout L, float iso) {
       fx = __ballot_sync(0xffffffffu, ex);
       fy = __ballot_sync(0xffffffffu, ey);
       fz = __ballot_sync(0xffffffffu, ez);
-      nt = sr_warp_sum_i(t);
+      // triangle counts are 0..5: three ballots + popc instead of a 5-step shuffle reduction
+      nt = __popc(__ballot_sync(0xffffffffu, t & 1)) + 2 * __popc(__ballot_sync(0xffffffffu, t & 2)) +
+           4 * __popc(__ballot_sync(0xffffffffu, t & 4));
       if (lane == 0) {
         L.fx[word] = fx; L.fy[word] = fy; L.fz[word] = fz;
       }
@@ -219,6 +251,7 @@ mc_classify_kernel(const float* __restrict__ sdf, McLayout L, float iso) {
       my_nv = __popc(fx) + __popc(fy) + __popc(fz);
       my_nt = (uint32_t)nt;
     }
+    cur = nxt; kw = nkw; j = nj; i = ni;
   }
   // warp-inclusive scan over the 32 words of this warp
   uint32_t sv = my_nv, st = my_nt;
@@ -297,7 +330,7 @@ __device__ __forceinline__ float edge_offset(float v1, float v2, float iso) {
 // vertex id of the edge (dir) owned by voxel (oi,oj,ok); -1 when that voxel is not a cell.
 __device__ __forceinline__ long long vertex_id(const McLayout& L, int oi, int oj, int ok, int dir) {
   if (oi >= L.nx - 1 || oj >= L.ny - 1 || ok >= L.nz - 1) return -1;
-  const long long word = ((long long)oi * L.ny + oj) * L.nwz + (ok >> 5);
+  const uint32_t word = ((uint32_t)oi * (uint32_t)L.ny + (uint32_t)oj) * (uint32_t)L.nwz + (uint32_t)(ok >> 5);
   const int bit = ok & 31;
   const uint32_t lt = (1u << bit) - 1u;
   const uint32_t fx = __ldg(L.fx + word), fy = __ldg(L.fy + word), fz = __ldg(L.fz + word);
@@ -334,9 +367,9 @@ mc_emit_kernel(const float* __restrict__ sdf, McLayout L, float iso, float xs, f
     if ((fx | fy | fz) == 0u && (tp & kHasTris) == 0u) continue;
     const uint32_t vbase = cta_v + __shfl_sync(0xffffffffu, wv, it);
     const uint32_t tbase = cta_t + (tp & ~kHasTris);
-    const int kw = (int)(word % L.nwz);
-    const long long ij = word / L.nwz;
-    const int j = (int)(ij % L.ny), i = (int)(ij / L.ny);
+    const int kw = (int)((uint32_t)word % (uint32_t)L.nwz);
+    const uint32_t ij = (uint32_t)word / (uint32_t)L.nwz;
+    const int j = (int)(ij % (uint32_t)L.ny), i = (int)(ij / (uint32_t)L.ny);
     const int k = kw * 32 + lane;
     float v[8];
     const int idx = load_cube(sdf, L.nx, L.ny, L.nz, i, j, k, iso, v);

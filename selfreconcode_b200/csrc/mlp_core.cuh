@@ -37,6 +37,14 @@ constexpr int kMaxIn = 296;            // max embedded input width kept in the s
 constexpr int kStashMax = 40;          // skip-connection stash: PE(3 + 6*6) = 39 -> 40
 
 // Shared-memory carve-up (dynamic smem, 16-byte aligned pieces).
+// One entry of the weight-streaming program of a tile: `nslices` bulk copies of `bytes` each.
+struct Step {
+  const char* src;
+  uint32_t bytes;
+  int nslices;
+};
+constexpr int kMaxSteps = 40;
+
 struct Smem {
   float* at;        // [kMaxK][kRowStride]
   float* wring;     // [kStages][kStageFloats]
@@ -44,10 +52,12 @@ struct Smem {
   float* res;       // [kTileRows][8] last-layer outputs (cols 0..7) per row
   uint64_t* full;   // [kStages]
   uint64_t* empty;  // [kStages]
+  Step* steps;      // [kMaxSteps] weight-streaming program (same for every tile)
+  int* nsteps;
 };
 constexpr size_t kSmemBytes = (size_t)kMaxK * kRowStride * 4 + (size_t)kStages * kStageFloats * 4 +
                               (size_t)kStashMax * kRowStride * 4 + (size_t)kTileRows * 8 * 4 +
-                              2 * kStages * 8 + 64;
+                              2 * kStages * 8 + kMaxSteps * sizeof(Step) + 64;
 
 __device__ __forceinline__ Smem carve(unsigned char* base) {
   Smem s;
@@ -61,6 +71,10 @@ __device__ __forceinline__ Smem carve(unsigned char* base) {
   base += (size_t)kTileRows * 8 * 4;
   s.full = reinterpret_cast<uint64_t*>(base);
   s.empty = s.full + kStages;
+  base += 2 * kStages * 8;
+  s.steps = reinterpret_cast<Step*>(base);
+  base += kMaxSteps * sizeof(Step);
+  s.nsteps = reinterpret_cast<int*>(base);
   return s;
 }
 
@@ -91,49 +105,75 @@ __device__ __forceinline__ void consumer_sync() {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Producer cursor (meaningful in thread 0 only): walks tiles x nets x layers x k-slices and
-// issues one bulk copy per call.  kStages-1 slices are issued up front; afterwards thread 0
-// issues one more each time its warp has finished a slice, so the slot it waits for is the
-// one every warp finished a full slice ago (loose coupling, 3 slices in flight).
+// Weight-streaming program + producer cursor.
+// The program (s.steps) lists, in consumption order, every GEMM of one tile: forward layers
+// stream W_T k-slices, backward layers stream the un-transposed copy.  The cursor (meaningful
+// in thread 0 only) walks tiles x steps x k-slices and issues one bulk copy per call: kStages-1
+// slices up front, then one more each time warp 0 has finished a slice, so the slot it waits
+// for is the one every warp finished a full slice ago (loose coupling, 3 slices in flight).
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void program_begin(const Smem& s) {
+  if (threadIdx.x == 0) *s.nsteps = 0;
+}
+__device__ __forceinline__ void program_add_fwd(const Smem& s, const sr_mlp_desc& net) {
+  if (threadIdx.x == 0) {
+    int n = *s.nsteps;
+    for (int l = 0; l < net.n_layers; ++l, ++n) {
+      const sr_mlp_layer& L = net.layer[l];
+      s.steps[n].src = reinterpret_cast<const char*>(L.wt);
+      s.steps[n].bytes = (uint32_t)(kKT * L.npad * 4);
+      s.steps[n].nslices = L.kpad / kKT;
+    }
+    *s.nsteps = n;
+  }
+}
+// backward GEMM of layer l: K = fan-out (padded to 8), N = fan-in (padded to 128)
+__device__ __forceinline__ int bwd_kpad(const sr_mlp_layer& L) { return (L.n + kKT - 1) / kKT * kKT; }
+__device__ __forceinline__ int bwd_npad(const sr_mlp_layer& L) { return (L.k + 127) / 128 * 128; }
+__device__ __forceinline__ void program_add_bwd(const Smem& s, const sr_mlp_desc& net) {
+  if (threadIdx.x == 0) {
+    int n = *s.nsteps;
+    for (int l = net.n_layers - 1; l >= 0; --l, ++n) {
+      const sr_mlp_layer& L = net.layer[l];
+      s.steps[n].src = reinterpret_cast<const char*>(L.wb);
+      s.steps[n].bytes = (uint32_t)(kKT * bwd_npad(L) * 4);
+      s.steps[n].nslices = bwd_kpad(L) / kKT;
+    }
+    *s.nsteps = n;
+  }
+}
+
 struct Prod {
   Pipe pp;
   long long tile, ntiles;
-  int stride, net_i, layer, slice, nnets;
-  const sr_mlp_desc* nets[2];
+  int stride, step, slice;
   bool done;
-  __device__ __forceinline__ void init(long long first_tile, long long ntiles_, int stride_,
-                                       const sr_mlp_desc* n0, const sr_mlp_desc* n1) {
+  __device__ __forceinline__ void init(long long first_tile, long long ntiles_, int stride_) {
     pp.slot = 0; pp.phase = 0;
     tile = first_tile; ntiles = ntiles_; stride = stride_;
-    net_i = 0; layer = 0; slice = 0;
-    nets[0] = n0; nets[1] = n1; nnets = n1 ? 2 : 1;
+    step = 0; slice = 0;
     done = first_tile >= ntiles_;
   }
   __device__ __forceinline__ void issue(const Smem& s) {
     if (done) return;
-    const sr_mlp_desc* net = nets[net_i];
-    const sr_mlp_layer& L = net->layer[layer];
-    const uint32_t bytes = (uint32_t)(kKT * L.npad * 4);
+    const Step st = s.steps[step];
     sr_mbar_wait(&s.empty[pp.slot], pp.phase ^ 1u);
-    sr_mbar_arrive_expect_tx(&s.full[pp.slot], bytes);
-    sr_bulk_g2s(s.wring + (size_t)pp.slot * kStageFloats,
-                reinterpret_cast<const char*>(L.wt) + (size_t)slice * bytes, bytes,
-                &s.full[pp.slot]);
+    sr_mbar_arrive_expect_tx(&s.full[pp.slot], st.bytes);
+    sr_bulk_g2s(s.wring + (size_t)pp.slot * kStageFloats, st.src + (size_t)slice * st.bytes,
+                st.bytes, &s.full[pp.slot]);
     pp.advance();
-    if (++slice == L.kpad / kKT) {
+    if (++slice == st.nslices) {
       slice = 0;
-      if (++layer == net->n_layers) {
-        layer = 0;
-        if (++net_i == nnets) {
-          net_i = 0;
-          tile += stride;
-          if (tile >= ntiles) done = true;
-        }
+      if (++step == *s.nsteps) {
+        step = 0;
+        tile += stride;
+        if (tile >= ntiles) done = true;
       }
     }
   }
+  // call after the program is complete; includes the barrier that publishes it
   __device__ __forceinline__ void prefill(const Smem& s) {
+    __syncthreads();
     if (threadIdx.x == 0)
       for (int i = 0; i < kStages - 1; ++i) issue(s);
   }
@@ -177,7 +217,10 @@ __device__ __forceinline__ void layer_gemm(const Smem& s, Pipe& cp, Prod& prod, 
     sr_mbar_wait(&s.full[cp.slot], cp.phase);
     const float* wst = s.wring + (size_t)cp.slot * kStageFloats + 4 * lane;
     const float* ak = arow + (size_t)sl * kKT * kRowStride;
-#pragma unroll
+    // Unroll by 2 only: one (kk) body is 128 FFMA + 6 LDS = ~2.1 KB of SASS; the fully unrolled
+    // 8-deep body (17 KB) overflowed the ~6 KB L0 instruction cache of the SM sub-partition and
+    // ncu showed 0.65 "no_instruction" stalls per issued instruction (profiles/r01_sdf_kernel.md).
+#pragma unroll 2
     for (int kk = 0; kk < kKT; ++kk) {
       const float4 a0 = *reinterpret_cast<const float4*>(ak + kk * kRowStride);
       const float4 a1 = *reinterpret_cast<const float4*>(ak + kk * kRowStride + 4);
@@ -209,11 +252,14 @@ struct LastOut {
   float* feat;        // global [P][nfeat] or nullptr: cols 1..nfeat of value rows
   int nfeat;
   const int* row_pt;  // smem: global point index per tile-local point (or -1)
+  float* dstash;      // global [n_layers][kMaxN][kTileRows] or nullptr: act'(z) of every hidden
+                      // layer, kept for a reverse-mode pass over the same tile (T = 0 only)
 };
+constexpr size_t kDstashLayerFloats = (size_t)kMaxN * kTileRows;
 
 template <int G, int T>
-__device__ __forceinline__ void layer_epilogue(const Smem& s, const sr_mlp_layer& L, bool last,
-                                               bool next_skip, int next_kpad, int d_in,
+__device__ __forceinline__ void layer_epilogue(const Smem& s, const sr_mlp_layer& L, int layer,
+                                               bool last, bool next_skip, int next_kpad, int d_in,
                                                const LastOut& lo, float (&acc)[8][16]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int CH = T + 1;
@@ -230,13 +276,20 @@ __device__ __forceinline__ void layer_epilogue(const Smem& s, const sr_mlp_layer
       if (col < L.n) {
         const float b = __ldg(L.bias + col);
         float o[8];
+        float dv[8];
 #pragma unroll
         for (int p = 0; p < PPT; ++p) {
           float d;
           const float z = acc[p * CH][c] + b;
           o[p * CH] = apply_act(L.act, z, d);
+          dv[p] = d;
 #pragma unroll
           for (int t = 1; t < CH; ++t) o[p * CH + t] = d * acc[p * CH + t][c];
+        }
+        if (T == 0 && !last && lo.dstash != nullptr) {
+          float* dd = lo.dstash + (size_t)layer * kDstashLayerFloats + (size_t)col * kTileRows + 8 * warp;
+          *reinterpret_cast<float4*>(dd) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+          *reinterpret_cast<float4*>(dd + 4) = make_float4(dv[4], dv[5], dv[6], dv[7]);
         }
         if (!last) {
           if (next_skip) {
@@ -301,20 +354,127 @@ __device__ __forceinline__ void run_net(const sr_mlp_desc& net, const Smem& s, P
     switch (L.npad >> 7) {
       case 1:
         layer_gemm<1>(s, cp, prod, L.kpad, L.npad, acc);
-        layer_epilogue<1, T>(s, L, last, next_skip, next_kpad, net.d_in, lo, acc);
+        layer_epilogue<1, T>(s, L, l, last, next_skip, next_kpad, net.d_in, lo, acc);
         break;
       case 2:
         layer_gemm<2>(s, cp, prod, L.kpad, L.npad, acc);
-        layer_epilogue<2, T>(s, L, last, next_skip, next_kpad, net.d_in, lo, acc);
+        layer_epilogue<2, T>(s, L, l, last, next_skip, next_kpad, net.d_in, lo, acc);
         break;
       case 3:
         layer_gemm<3>(s, cp, prod, L.kpad, L.npad, acc);
-        layer_epilogue<3, T>(s, L, last, next_skip, next_kpad, net.d_in, lo, acc);
+        layer_epilogue<3, T>(s, L, l, last, next_skip, next_kpad, net.d_in, lo, acc);
         break;
       default:
         layer_gemm<4>(s, cp, prod, L.kpad, L.npad, acc);
-        layer_epilogue<4, T>(s, L, last, next_skip, next_kpad, net.d_in, lo, acc);
+        layer_epilogue<4, T>(s, L, l, last, next_skip, next_kpad, net.d_in, lo, acc);
         break;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Reverse-mode pass over the tile that run_net<0> just evaluated with a derivative stash.
+//   in : A_T rows [0, bwd_kpad(last)) hold the cotangent of the net's outputs (row k = output k)
+//   out: A_T rows [0, d_in) hold d(sum_k cot_k * out_k) / d(embedded input)   (skip path included)
+// Backward GEMM of layer l: g_in[rows x fan_in] = delta_l[rows x fan_out] * W_l, streamed from the
+// un-transposed padded copy `wb`; delta_{l-1} = g_in * act'_{l-1} (and the /sqrt(2) of a skip).
+// ---------------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ void bwd_epilogue(const Smem& s, const sr_mlp_desc& net, int l,
+                                             const float* dstash, float (&acc)[8][16]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const sr_mlp_layer& L = net.layer[l];
+  const float inv_div = 1.41421356237309504880f;
+  const bool skip = L.skip != 0;
+  const int n_prev = l > 0 ? net.layer[l - 1].n : 0;         // width of the previous layer's output
+  const int next_k = l > 0 ? bwd_kpad(net.layer[l - 1]) : 0;  // K of the next backward GEMM
+  consumer_sync();
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = 4 * g + i;
+      const int col = g * 128 + 4 * lane + i;
+      float o[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) o[r] = acc[r][c];
+      if (skip) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) o[r] = __fdiv_rn(o[r], inv_div);
+      }
+      if (l == 0) {
+        if (col < L.k) {
+          float* dst = s.at + (size_t)col * kRowStride + 8 * warp;
+          if (col < kStashMax) {  // add the gradient that arrived through the skip connection
+            const float* sg = s.stash + (size_t)col * kRowStride + 8 * warp;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) o[r] += sg[r];
+          }
+          *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+      } else if (col < n_prev) {
+        const float* dd = dstash + (size_t)(l - 1) * kDstashLayerFloats + (size_t)col * kTileRows + 8 * warp;
+        const float4 d0 = *reinterpret_cast<const float4*>(dd);
+        const float4 d1 = *reinterpret_cast<const float4*>(dd + 4);
+        float* dst = s.at + (size_t)col * kRowStride + 8 * warp;
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0] * d0.x, o[1] * d0.y, o[2] * d0.z, o[3] * d0.w);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4] * d1.x, o[5] * d1.y, o[6] * d1.z, o[7] * d1.w);
+      } else {
+        if (skip && col < n_prev + net.d_in && col - n_prev < kStashMax) {
+          float* sg = s.stash + (size_t)(col - n_prev) * kRowStride + 8 * warp;
+          *reinterpret_cast<float4*>(sg) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(sg + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+        if (col < next_k) {  // k-padding of the next backward GEMM
+          float* dst = s.at + (size_t)col * kRowStride + 8 * warp;
+          *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+  }
+  consumer_sync();
+}
+
+// zero the skip-gradient stash (call before run_net_bwd on a net; cheap: 40 x 64 floats)
+__device__ __forceinline__ void bwd_clear_stash(const Smem& s) {
+  for (int idx = threadIdx.x; idx < kStashMax * (kTileRows / 4); idx += kConsumerThreads) {
+    const int k = idx / (kTileRows / 4), r4 = (idx % (kTileRows / 4)) * 4;
+    *reinterpret_cast<float4*>(s.stash + (size_t)k * kRowStride + r4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+__device__ __forceinline__ void run_net_bwd(const sr_mlp_desc& net, const Smem& s, Pipe& cp,
+                                            Prod& prod, const float* dstash) {
+  float acc[8][16];
+  for (int l = net.n_layers - 1; l >= 0; --l) {
+    const sr_mlp_layer& L = net.layer[l];
+    const int kp = bwd_kpad(L), np = bwd_npad(L);
+    switch (np >> 7) {
+      case 1: layer_gemm<1>(s, cp, prod, kp, np, acc); bwd_epilogue<1>(s, net, l, dstash, acc); break;
+      case 2: layer_gemm<2>(s, cp, prod, kp, np, acc); bwd_epilogue<2>(s, net, l, dstash, acc); break;
+      case 3: layer_gemm<3>(s, cp, prod, kp, np, acc); bwd_epilogue<3>(s, net, l, dstash, acc); break;
+      default: layer_gemm<4>(s, cp, prod, kp, np, acc); bwd_epilogue<4>(s, net, l, dstash, acc); break;
+    }
+  }
+}
+
+// chain rule through the positional encoding: rows [0, 3+6L) of A_T hold dL/d(embedding);
+// returns dL/dx for tile row `row` at point x.
+__device__ __forceinline__ void embed_backward(const float* at, int row, const float x[3],
+                                               int multires, const float* pe_w, float g[3]) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j) g[j] = at[(size_t)j * kRowStride + row];
+  float freq = 1.0f;
+  for (int b = 0; b < multires; ++b, freq *= 2.0f) {
+    const float w = pe_w[b] * freq;
+    const int ks = 3 + 6 * b, kc = ks + 3;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float sn, cs;
+      sincosf(x[j] * freq, &sn, &cs);
+      g[j] += w * (cs * at[(size_t)(ks + j) * kRowStride + row] - sn * at[(size_t)(kc + j) * kRowStride + row]);
     }
   }
 }

@@ -236,6 +236,11 @@ __device__ __forceinline__ void deform_finish(const TileCtx& c, const sr_lbs_par
         a[AUX_OFF + j] = off[j];
         a[AUX_CI + j] = __int_as_float(ci[j]);
       }
+      if (T == 0) {
+        // reverse-mode callers need M = dD/dp' (the translator Jacobian comes from the backward sweep)
+#pragma unroll
+        for (int i = 0; i < 9; ++i) a[AUX_J + i] = M[i];
+      }
       if (T == 3) {
         // dp'/dp = I + Joff, Joff[m][cc] = d off_m / d p_cc = res[row+1+cc][m]
         float Q[9];
@@ -270,6 +275,19 @@ __device__ __forceinline__ void sdf_finish(const TileCtx& c) {
   }
 }
 
+// identity deformer: D(p) = p, J = I
+template <int T>
+__device__ __forceinline__ void identity_deform(const TileCtx& c) {
+  constexpr int PTS = kTileRows / (T + 1);
+  if (threadIdx.x < PTS) {
+    float* a = c.aux + threadIdx.x * kAuxStride;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { a[AUX_D + j] = a[AUX_P + j]; a[AUX_OFF + j] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) a[AUX_J + i] = (i % 4 == 0) ? 1.f : 0.f;
+  }
+}
+
 // =============================================================================================
 // Kernels
 // =============================================================================================
@@ -292,13 +310,15 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_kernel(const __grid_constant_
   const long long ntiles = (args.P + PTS - 1) / PTS;
   Pipe cp{0, 0};
   Prod prod;
-  prod.init(blockIdx.x, ntiles, gridDim.x, &args.net, nullptr);
+  program_begin(c.s);
+  program_add_fwd(c.s, args.net);
+  prod.init(blockIdx.x, ntiles, gridDim.x);
   prod.prefill(c.s);
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     load_points<T>(c, tile, args.P, nullptr, args.pts, nullptr, 0);
     consumer_sync();
     prologue_pe<T>(c, args.net, nullptr, 0);
-    LastOut lo{args.feat, args.nfeat, c.row_pt};
+    LastOut lo{args.feat, args.nfeat, c.row_pt, nullptr};
     run_net<T>(args.net, c.s, cp, prod, lo);
     if (threadIdx.x < PTS) {
       const int gp = c.row_pt[threadIdx.x];
@@ -341,13 +361,15 @@ deform_kernel(const __grid_constant__ DeformArgs args) {
   const long long ntiles = (args.P + PTS - 1) / PTS;
   Pipe cp{0, 0};
   Prod prod;
-  prod.init(blockIdx.x, ntiles, gridDim.x, &args.net, nullptr);
+  program_begin(c.s);
+  program_add_fwd(c.s, args.net);
+  prod.init(blockIdx.x, ntiles, gridDim.x);
   prod.prefill(c.s);
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     load_points<T>(c, tile, args.P, nullptr, args.pts, args.batch_inds, args.pts_per_frame);
     consumer_sync();
     prologue_pe<T>(c, args.net, args.conds, args.condlen);
-    LastOut lo{nullptr, 0, c.row_pt};
+    LastOut lo{nullptr, 0, c.row_pt, nullptr};
     run_net<T>(args.net, c.s, cp, prod, lo);
     deform_finish<T>(c, args.has_lbs ? &args.lbs : nullptr);
     consumer_sync();
@@ -390,7 +412,9 @@ render_kernel(const __grid_constant__ RenderArgs args) {
   const long long ntiles = (args.P + kTileRows - 1) / kTileRows;
   Pipe cp{0, 0};
   Prod prod;
-  prod.init(blockIdx.x, ntiles, gridDim.x, &args.net, nullptr);
+  program_begin(c.s);
+  program_add_fwd(c.s, args.net);
+  prod.init(blockIdx.x, ntiles, gridDim.x);
   prod.prefill(c.s);
   const sr_mlp_desc& net = args.net;
   const int pe_dim = 3 + 6 * net.multires;  // embedded view direction
@@ -427,7 +451,7 @@ render_kernel(const __grid_constant__ RenderArgs args) {
       c.s.at[(size_t)(k0 + kf) * kRowStride + row] = v;
     }
     consumer_sync();
-    LastOut lo{nullptr, 0, c.row_pt};
+    LastOut lo{nullptr, 0, c.row_pt, nullptr};
     run_net<0>(net, c.s, cp, prod, lo);
     if (threadIdx.x < kTileRows) {
       const int gp = c.row_pt[threadIdx.x];
@@ -449,6 +473,7 @@ struct TraceArgs {
   sr_mlp_desc dnet;
   sr_lbs_params lbs;
   int has_lbs;
+  int has_dnet;  // 0: identity deformer D(p) = p (BASELINE config 1)
   sr_trace_params tp;
   float* pts;
   const float* rays;
@@ -474,9 +499,12 @@ trace_kernel(const __grid_constant__ TraceArgs args) {
   const long long ntiles = (count + PTS - 1) / PTS;
   Pipe cp{0, 0};
   Prod prod;
-  prod.init(blockIdx.x, ntiles, gridDim.x, &args.sdf, &args.dnet);
+  program_begin(c.s);
+  program_add_fwd(c.s, args.sdf);
+  if (args.has_dnet) program_add_fwd(c.s, args.dnet);
+  prod.init(blockIdx.x, ntiles, gridDim.x);
   prod.prefill(c.s);
-  const LastOut lo{nullptr, 0, c.row_pt};
+  const LastOut lo{nullptr, 0, c.row_pt, nullptr};
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     load_points<T>(c, tile, count, args.active_in, args.pts, args.batch_inds, 0);
     consumer_sync();
@@ -484,9 +512,13 @@ trace_kernel(const __grid_constant__ TraceArgs args) {
     run_net<T>(args.sdf, c.s, cp, prod, lo);
     sdf_finish<T>(c);
     consumer_sync();
-    prologue_pe<T>(c, args.dnet, args.conds, args.condlen);
-    run_net<T>(args.dnet, c.s, cp, prod, lo);
-    deform_finish<T>(c, args.has_lbs ? &args.lbs : nullptr);
+    if (args.has_dnet) {
+      prologue_pe<T>(c, args.dnet, args.conds, args.condlen);
+      run_net<T>(args.dnet, c.s, cp, prod, lo);
+      deform_finish<T>(c, args.has_lbs ? &args.lbs : nullptr);
+    } else {
+      identity_deform<T>(c);
+    }
     consumer_sync();
     if (threadIdx.x < PTS) {
       const float* a = c.aux + threadIdx.x * kAuxStride;
@@ -535,6 +567,154 @@ trace_kernel(const __grid_constant__ TraceArgs args) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Reverse-mode tracer step: 64 rays per tile, value-only forward sweeps that stash act'(z),
+// then one backward sweep per network with the loss cotangent.  Same update as trace_kernel.
+// ---------------------------------------------------------------------------------------------
+struct TraceRevArgs {
+  TraceArgs t;
+  float* scratch;  // [gridDim.x][2][SR_MLP_MAX_LAYERS][kMaxN][kTileRows]
+};
+constexpr size_t kScratchPerCta = 2 * (size_t)SR_MLP_MAX_LAYERS * kDstashLayerFloats;
+
+__global__ void __launch_bounds__(kThreads, 1)
+trace_rev_kernel(const __grid_constant__ TraceRevArgs ra) {
+  const TraceArgs& args = ra.t;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TileCtx c = make_ctx(smem_raw);
+  pipe_init(c.s);
+  constexpr int T = 0, PTS = kTileRows;
+  const long long count = args.active_in ? (long long)args.counters[args.iter] : args.P;
+  const long long ntiles = (count + PTS - 1) / PTS;
+  Pipe cp{0, 0};
+  Prod prod;
+  program_begin(c.s);
+  program_add_fwd(c.s, args.sdf);
+  if (args.has_dnet) program_add_fwd(c.s, args.dnet);
+  if (args.do_update) {
+    program_add_bwd(c.s, args.sdf);
+    if (args.has_dnet) program_add_bwd(c.s, args.dnet);
+  }
+  prod.init(blockIdx.x, ntiles, gridDim.x);
+  prod.prefill(c.s);
+  float* ds_sdf = ra.scratch + (size_t)blockIdx.x * kScratchPerCta;
+  float* ds_def = ds_sdf + (size_t)SR_MLP_MAX_LAYERS * kDstashLayerFloats;
+  const int warp = threadIdx.x >> 5;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    load_points<T>(c, tile, count, args.active_in, args.pts, args.batch_inds, 0);
+    consumer_sync();
+    // ---- forward sweeps
+    prologue_pe<T>(c, args.sdf, nullptr, 0);
+    {
+      const LastOut lo{nullptr, 0, c.row_pt, args.do_update ? ds_sdf : nullptr};
+      run_net<T>(args.sdf, c.s, cp, prod, lo);
+    }
+    sdf_finish<T>(c);
+    consumer_sync();
+    if (args.has_dnet) {
+      prologue_pe<T>(c, args.dnet, args.conds, args.condlen);
+      const LastOut lo{nullptr, 0, c.row_pt, args.do_update ? ds_def : nullptr};
+      run_net<T>(args.dnet, c.s, cp, prod, lo);
+      deform_finish<T>(c, args.has_lbs ? &args.lbs : nullptr);
+    } else {
+      identity_deform<T>(c);
+    }
+    consumer_sync();
+    // ---- test, loss, cotangents (one thread per ray)
+    if (threadIdx.x < PTS) {
+      float* a = c.aux + threadIdx.x * kAuxStride;
+      const int gp = __float_as_int(a[AUX_GP]);
+      float cot_f = 0.f, u[3] = {0.f, 0.f, 0.f}, loss = 0.f;
+      int state = 0;  // 0: padding / done, 1: needs update
+      if (gp >= 0) {
+        const float f = a[AUX_F];
+        const float vx = args.rays[(size_t)gp * 3], vy = args.rays[(size_t)gp * 3 + 1],
+                    vz = args.rays[(size_t)gp * 3 + 2];
+        const float ux = a[AUX_D] - args.tp.cam_pos[0], uy = a[AUX_D + 1] - args.tp.cam_pos[1],
+                    uz = a[AUX_D + 2] - args.tp.cam_pos[2];
+        const float cx = uy * vz - uz * vy, cy = uz * vx - ux * vz, cz = ux * vy - uy * vx;
+        const float n_up = sqrtf(cx * cx + cy * cy + cz * cz);
+        const float n_u = sqrtf(ux * ux + uy * uy + uz * uz);
+        const float sang = n_up / n_u;
+        const float ang = asinf(sang) * 180.0f / 3.14159265358979323846f;
+        const bool done = (fabsf(f) < args.tp.dthreshold) && (ang < args.tp.athreshold);
+        if (done) {
+          args.converged[gp] = 1;
+        } else if (args.do_update) {
+          state = 1;
+          loss = args.tp.w1 * fabsf(f) + args.tp.w2 * fabsf(sang);
+          float q[3] = {0.f, 0.f, 0.f};
+          if (n_up > 0.f) {
+            const float wx = vy * cz - vz * cy, wy = vz * cx - vx * cz, wz = vx * cy - vy * cx;
+            const float i1 = 1.0f / (n_up * n_u), i2 = n_up / (n_u * n_u * n_u);
+            q[0] = wx * i1 - ux * i2; q[1] = wy * i1 - uy * i2; q[2] = wz * i1 - uz * i2;
+          }
+          cot_f = args.tp.w1 * (f > 0.f ? 1.f : (f < 0.f ? -1.f : 0.f));
+          // u = w2 * M^T q : cotangent of p' = p + offset (also the direct dD/dp term)
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+            u[j] = args.tp.w2 * (a[AUX_J + j] * q[0] + a[AUX_J + 3 + j] * q[1] + a[AUX_J + 6 + j] * q[2]);
+        }
+      }
+      a[AUX_F] = cot_f;                 // slots reused: cotangent of f
+      a[AUX_D] = u[0]; a[AUX_D + 1] = u[1]; a[AUX_D + 2] = u[2];
+      a[AUX_OFF] = loss;
+      a[AUX_OFF + 1] = __int_as_float(state);
+    }
+    consumer_sync();
+    if (args.do_update) {
+      // ---- backward sweep through the SDF: cotangent w1*sign(f) on output 0
+      {
+        const int kp = bwd_kpad(args.sdf.layer[args.sdf.n_layers - 1]);
+        for (int idx = threadIdx.x; idx < kp * kTileRows; idx += kConsumerThreads) {
+          const int k = idx / kTileRows, row = idx % kTileRows;
+          c.s.at[(size_t)k * kRowStride + row] = (k == 0) ? c.aux[row * kAuxStride + AUX_F] : 0.f;
+        }
+        bwd_clear_stash(c.s);
+        run_net_bwd(args.sdf, c.s, cp, prod, ds_sdf);  // epilogues carry the barriers
+      }
+      if (threadIdx.x < PTS) {
+        float* a = c.aux + threadIdx.x * kAuxStride;
+        const float x[3] = {a[AUX_P], a[AUX_P + 1], a[AUX_P + 2]};
+        float g[3];
+        embed_backward(c.s.at, threadIdx.x, x, args.sdf.multires, args.sdf.pe_w, g);
+        a[AUX_GF] = g[0]; a[AUX_GF + 1] = g[1]; a[AUX_GF + 2] = g[2];
+      }
+      consumer_sync();
+      // ---- backward sweep through the translator: cotangent u on its 3 outputs
+      if (args.has_dnet) {
+        const int kp = bwd_kpad(args.dnet.layer[args.dnet.n_layers - 1]);
+        for (int idx = threadIdx.x; idx < kp * kTileRows; idx += kConsumerThreads) {
+          const int k = idx / kTileRows, row = idx % kTileRows;
+          c.s.at[(size_t)k * kRowStride + row] = (k < 3) ? c.aux[row * kAuxStride + AUX_D + k] : 0.f;
+        }
+        bwd_clear_stash(c.s);
+        run_net_bwd(args.dnet, c.s, cp, prod, ds_def);
+      }
+      if (threadIdx.x < PTS) {
+        float* a = c.aux + threadIdx.x * kAuxStride;
+        const int gp = __float_as_int(a[AUX_GP]);
+        if (gp >= 0 && __float_as_int(a[AUX_OFF + 1]) == 1) {
+          const float x[3] = {a[AUX_P], a[AUX_P + 1], a[AUX_P + 2]};
+          float g[3] = {a[AUX_GF] + a[AUX_D], a[AUX_GF + 1] + a[AUX_D + 1], a[AUX_GF + 2] + a[AUX_D + 2]};
+          if (args.has_dnet) {
+            float gd[3];
+            embed_backward(c.s.at, threadIdx.x, x, args.dnet.multires, args.dnet.pe_w, gd);
+            g[0] += gd[0]; g[1] += gd[1]; g[2] += gd[2];
+          }
+          const float t = -a[AUX_OFF] / (g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) args.pts[(size_t)gp * 3 + j] = x[j] + t * g[j];
+          const int slot = atomicAdd(&args.counters[args.iter + 1], 1);
+          args.active_out[slot] = gp;
+        }
+      }
+    }
+    consumer_sync();
+  }
+  (void)warp;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Shading geometry at surface points (infer path).
 // ---------------------------------------------------------------------------------------------
 struct ShadeArgs {
@@ -542,6 +722,7 @@ struct ShadeArgs {
   sr_mlp_desc dnet;
   sr_lbs_params lbs;
   int has_lbs;
+  int has_dnet;
   const float* pts;
   const float* rays;
   const int64_t* batch_inds;
@@ -565,24 +746,29 @@ shade_kernel(const __grid_constant__ ShadeArgs args) {
   const long long ntiles = (args.P + PTS - 1) / PTS;
   Pipe cp{0, 0};
   Prod prod;
-  prod.init(blockIdx.x, ntiles, gridDim.x, &args.sdf, &args.dnet);
+  program_begin(c.s);
+  program_add_fwd(c.s, args.sdf);
+  if (args.has_dnet) program_add_fwd(c.s, args.dnet);
+  prod.init(blockIdx.x, ntiles, gridDim.x);
   prod.prefill(c.s);
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     load_points<T>(c, tile, args.P, nullptr, args.pts, args.batch_inds, 0);
     consumer_sync();
     prologue_pe<T>(c, args.sdf, nullptr, 0);
     {
-      const LastOut lo{args.feat, args.nfeat, c.row_pt};
+      const LastOut lo{args.feat, args.nfeat, c.row_pt, nullptr};
       run_net<T>(args.sdf, c.s, cp, prod, lo);
     }
     sdf_finish<T>(c);
     consumer_sync();
-    prologue_pe<T>(c, args.dnet, args.conds, args.condlen);
-    {
-      const LastOut lo{nullptr, 0, c.row_pt};
+    if (args.has_dnet) {
+      prologue_pe<T>(c, args.dnet, args.conds, args.condlen);
+      const LastOut lo{nullptr, 0, c.row_pt, nullptr};
       run_net<T>(args.dnet, c.s, cp, prod, lo);
+      deform_finish<T>(c, args.has_lbs ? &args.lbs : nullptr);
+    } else {
+      identity_deform<T>(c);
     }
-    deform_finish<T>(c, args.has_lbs ? &args.lbs : nullptr);
     consumer_sync();
     if (threadIdx.x < PTS) {
       const float* a = c.aux + threadIdx.x * kAuxStride;
@@ -633,7 +819,8 @@ shade_kernel(const __grid_constant__ ShadeArgs args) {
 // weight-norm fold + transpose + pad: one warp per output row n.
 __global__ void __launch_bounds__(256)
 fold_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ b,
-            int n, int k, int npad, int kpad, float* __restrict__ wt, float* __restrict__ bias) {
+            int n, int k, int npad, int kpad, float* __restrict__ wt, float* __restrict__ bias,
+            float* __restrict__ wb, int wb_rows, int wb_cols) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= npad) return;
   const int row = warp;
@@ -650,7 +837,10 @@ fold_kernel(const float* __restrict__ v, const float* __restrict__ g, const floa
     float w = 0.f;
     if (row < n && j < k) w = g ? v[(size_t)row * k + j] * scale : v[(size_t)row * k + j];
     wt[(size_t)j * npad + row] = w;
+    if (wb && row < wb_rows) wb[(size_t)row * wb_cols + j] = w;  // un-transposed copy (j < kpad <= wb_cols)
   }
+  if (wb && row < wb_rows)
+    for (int j = kpad + lane; j < wb_cols; j += 32) wb[(size_t)row * wb_cols + j] = 0.f;
   if (lane == 0) bias[row] = (row < n && b) ? b[row] : 0.f;
 }
 
@@ -773,11 +963,13 @@ int grid_for_tiles(long long ntiles) {
 extern "C" {
 
 int sr_fold_linear(const float* v, const float* g, const float* b, int n, int k, int npad,
-                   int kpad, float* wt, float* bias_out, cudaStream_t s) {
+                   int kpad, float* wt, float* bias_out, float* wb, cudaStream_t s) {
   if (!v || !wt || !bias_out || n <= 0 || k <= 0 || npad < n || kpad < k) return SR_EINVAL;
   const int warps_per_block = 8;
+  const int wb_rows = (n + kKT - 1) / kKT * kKT, wb_cols = (k + 127) / 128 * 128;
+  if (wb_rows > npad) return SR_EINVAL;
   fold_kernel<<<sr_div_up(npad, warps_per_block), 256, 0, s>>>(v, g, b, n, k, npad, kpad, wt,
-                                                               bias_out);
+                                                               bias_out, wb, wb_rows, wb_cols);
   return sr_launch_status();
 }
 
@@ -882,16 +1074,19 @@ int sr_trace_step(const sr_mlp_desc* sdf, const sr_mlp_desc* dnet, const sr_lbs_
                   uint8_t* converged, cudaStream_t s) {
   int rc = validate_net(sdf, 3);
   if (rc) return rc;
-  if ((rc = validate_net(dnet, 3))) return rc;
+  if (dnet && (rc = validate_net(dnet, 3))) return rc;
+  if (!dnet && lbs) return SR_EINVAL;
   if ((rc = check_lbs(lbs))) return rc;
   if (!tp || P < 0 || P > 0x7fffffffLL || iter < 0) return SR_EINVAL;
   if (P == 0) return SR_OK;
   if (!pts || !rays || !counters || !converged) return SR_EINVAL;
   if (sdf->d_in != 3 + 6 * sdf->multires) return SR_EINVAL;
-  if (dnet->d_in != 3 + 6 * dnet->multires + condlen) return SR_EINVAL;
-  if (dnet->layer[dnet->n_layers - 1].n != 3) return SR_EINVAL;
+  if (dnet && dnet->d_in != 3 + 6 * dnet->multires + condlen) return SR_EINVAL;
+  if (dnet && dnet->layer[dnet->n_layers - 1].n != 3) return SR_EINVAL;
   TraceArgs a;
-  a.sdf = *sdf; a.dnet = *dnet;
+  a.sdf = *sdf;
+  a.has_dnet = dnet ? 1 : 0;
+  if (dnet) a.dnet = *dnet;
   a.has_lbs = lbs ? 1 : 0;
   if (lbs) a.lbs = *lbs;
   a.tp = *tp; a.pts = pts; a.rays = rays; a.batch_inds = batch_inds; a.conds = conds;
@@ -903,22 +1098,67 @@ int sr_trace_step(const sr_mlp_desc* sdf, const sr_mlp_desc* dnet, const sr_lbs_
   return sr_launch_status();
 }
 
+int64_t sr_trace_scratch_bytes(void) {
+  return (int64_t)SR_NUM_SMS_B200 * (int64_t)kScratchPerCta * (int64_t)sizeof(float);
+}
+
+int sr_trace_step_rev(const sr_mlp_desc* sdf, const sr_mlp_desc* dnet, const sr_lbs_params* lbs,
+                      const sr_trace_params* tp, float* pts, const float* rays,
+                      const int64_t* batch_inds, const float* conds, int condlen, int64_t P,
+                      const int32_t* active_in, int32_t* active_out, int32_t* counters, int iter,
+                      uint8_t* converged, float* scratch, cudaStream_t s) {
+  int rc = validate_net(sdf, 0);
+  if (rc) return rc;
+  if (dnet && (rc = validate_net(dnet, 0))) return rc;
+  if (!dnet && lbs) return SR_EINVAL;
+  if ((rc = check_lbs(lbs))) return rc;
+  if (!tp || P < 0 || P > 0x7fffffffLL || iter < 0) return SR_EINVAL;
+  if (P == 0) return SR_OK;
+  if (!pts || !rays || !counters || !converged || !scratch) return SR_EINVAL;
+  if (sdf->d_in != 3 + 6 * sdf->multires) return SR_EINVAL;
+  if (dnet && dnet->d_in != 3 + 6 * dnet->multires + condlen) return SR_EINVAL;
+  if (dnet && dnet->layer[dnet->n_layers - 1].n != 3) return SR_EINVAL;
+  for (int l = 0; l < sdf->n_layers; ++l)
+    if (!sdf->layer[l].wb) return SR_EINVAL;
+  if (dnet)
+    for (int l = 0; l < dnet->n_layers; ++l)
+      if (!dnet->layer[l].wb) return SR_EINVAL;
+  TraceRevArgs a;
+  a.t.sdf = *sdf;
+  a.t.has_dnet = dnet ? 1 : 0;
+  if (dnet) a.t.dnet = *dnet;
+  a.t.has_lbs = lbs ? 1 : 0;
+  if (lbs) a.t.lbs = *lbs;
+  a.t.tp = *tp; a.t.pts = pts; a.t.rays = rays; a.t.batch_inds = batch_inds; a.t.conds = conds;
+  a.t.condlen = condlen; a.t.P = P; a.t.active_in = active_in; a.t.active_out = active_out;
+  a.t.counters = counters; a.t.iter = iter; a.t.do_update = active_out ? 1 : 0;
+  a.t.converged = converged;
+  a.scratch = scratch;
+  if ((rc = set_smem(trace_rev_kernel))) return rc;
+  const long long nt = (P + kTileRows - 1) / kTileRows;
+  trace_rev_kernel<<<grid_for_tiles(nt), kThreads, kDynSmem, s>>>(a);
+  return sr_launch_status();
+}
+
 int sr_shade_geometry(const sr_mlp_desc* sdf, const sr_mlp_desc* dnet, const sr_lbs_params* lbs,
                       const float* pts, const float* rays, const int64_t* batch_inds,
                       const float* conds, int condlen, int64_t P, float* normals, float* crays,
                       float* feat, int nfeat, float* dpos, uint8_t* inv_ok, cudaStream_t s) {
   int rc = validate_net(sdf, 3);
   if (rc) return rc;
-  if ((rc = validate_net(dnet, 3))) return rc;
+  if (dnet && (rc = validate_net(dnet, 3))) return rc;
+  if (!dnet && lbs) return SR_EINVAL;
   if ((rc = check_lbs(lbs))) return rc;
   if (P < 0 || P > 0x7fffffffLL) return SR_EINVAL;
   if (P == 0) return SR_OK;
   if (!pts || !rays || !normals || !crays) return SR_EINVAL;
   if (sdf->d_in != 3 + 6 * sdf->multires) return SR_EINVAL;
-  if (dnet->d_in != 3 + 6 * dnet->multires + condlen) return SR_EINVAL;
+  if (dnet && dnet->d_in != 3 + 6 * dnet->multires + condlen) return SR_EINVAL;
   if (feat && (nfeat <= 0 || nfeat + 1 > sdf->layer[sdf->n_layers - 1].n)) return SR_EINVAL;
   ShadeArgs a;
-  a.sdf = *sdf; a.dnet = *dnet;
+  a.sdf = *sdf;
+  a.has_dnet = dnet ? 1 : 0;
+  if (dnet) a.dnet = *dnet;
   a.has_lbs = lbs ? 1 : 0;
   if (lbs) a.lbs = *lbs;
   a.pts = pts; a.rays = rays; a.batch_inds = batch_inds; a.conds = conds; a.condlen = condlen;

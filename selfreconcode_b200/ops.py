@@ -264,16 +264,18 @@ class FusedMLP:
                     raise RuntimeError("FusedMLP: layer %dx%d exceeds the 512-wide engine" % (n, k))
                 wt = torch.empty((kpad, npad), dtype=torch.float32, device=self.device)
                 bias = torch.empty((npad,), dtype=torch.float32, device=self.device)
+                wb = torch.empty((_pad(n, 8), _pad(k, 128)), dtype=torch.float32, device=self.device)
                 g = L.get("g")
                 b = L.get("b")
                 g = g.detach().contiguous().float().view(-1) if g is not None else None
                 b = b.detach().contiguous().float() if b is not None else None
                 check(lib.sr_fold_linear(_p(v), _p(g), _p(b), n, k, npad, kpad, _p(wt), _p(bias),
-                                         _stream()), "fold_linear")
-                bufs += [wt, bias, v, g, b]
+                                         _p(wb), _stream()), "fold_linear")
+                bufs += [wt, bias, v, g, b, wb]
                 ly = d.layer[i]
                 ly.wt = wt.data_ptr()
                 ly.bias = bias.data_ptr()
+                ly.wb = wb.data_ptr()
                 ly.k, ly.n, ly.kpad, ly.npad = k, n, kpad, npad
                 ly.act = int(L["act"])
                 ly.skip = 1 if L.get("skip") else 0
@@ -422,9 +424,22 @@ def render_forward(net, pts, normals, views, feat):
     return rgb
 
 
+_scratch = {}
+
+
+def _trace_scratch(dev):
+    """act'(z) stash of the reverse-mode tracer (one region per SM, reused across calls on the
+    same stream order)."""
+    key = dev.index
+    if key not in _scratch:
+        n = _lib.load().sr_trace_scratch_bytes()
+        _scratch[key] = torch.empty((n // 4,), dtype=torch.float32, device=dev)
+    return _scratch[key]
+
+
 def trace_surface_points(sdf_net, def_net, lbs, cam_pos, rays, init_pts, batch_inds, conds,
                          dthreshold=5e-5, athreshold=0.02, w1=3.05, w2=1.0, times=5,
-                         return_counters=False):
+                         return_counters=False, mode="reverse"):
     """OptimizeSurfacePs (utils/FindSurfacePs.py:114-163): returns (points, converged).
     times+1 launches are enqueued back to back; nothing syncs the host."""
     _need_cuda(rays, init_pts)
@@ -447,14 +462,22 @@ def trace_surface_points(sdf_net, def_net, lbs, cam_pos, rays, init_pts, batch_i
         tp.cam_pos[i] = cp[i]
     tp.dthreshold, tp.athreshold, tp.w1, tp.w2 = float(dthreshold), float(athreshold), float(w1), float(w2)
     lib = _lib.load()
+    dref = C.byref(def_net.desc) if def_net is not None else None
     with torch.cuda.device(dev):
+        scratch = _trace_scratch(dev) if mode == "reverse" else None
         for it in range(times + 1):
             a_in = lists[(it + 1) & 1] if it > 0 else None
             a_out = lists[it & 1] if it < times else None
-            check(lib.sr_trace_step(C.byref(sdf_net.desc), C.byref(def_net.desc), _lbs_ref(lbs),
-                                    C.byref(tp), _p(pts), _p(rays), _p(bi), _p(conds), condlen, P,
-                                    _p(a_in), _p(a_out), _p(counters), it, _p(conv), _stream()),
-                  "trace_step")
+            if mode == "reverse":
+                check(lib.sr_trace_step_rev(C.byref(sdf_net.desc), dref, _lbs_ref(lbs), C.byref(tp),
+                                            _p(pts), _p(rays), _p(bi), _p(conds), condlen, P, _p(a_in),
+                                            _p(a_out), _p(counters), it, _p(conv), _p(scratch),
+                                            _stream()), "trace_step_rev")
+            else:
+                check(lib.sr_trace_step(C.byref(sdf_net.desc), dref, _lbs_ref(lbs), C.byref(tp),
+                                        _p(pts), _p(rays), _p(bi), _p(conds), condlen, P, _p(a_in),
+                                        _p(a_out), _p(counters), it, _p(conv), _stream()),
+                      "trace_step")
     if return_counters:  # counters[it] = rays updated in iteration it (it = 1..times)
         return pts, conv, counters
     return pts, conv
@@ -476,7 +499,8 @@ def shade_geometry(sdf_net, def_net, lbs, pts, rays, batch_inds, conds, nfeat=0,
     ok = torch.empty((P,), dtype=torch.bool, device=dev)
     lib = _lib.load()
     with torch.cuda.device(dev):
-        check(lib.sr_shade_geometry(C.byref(sdf_net.desc), C.byref(def_net.desc), _lbs_ref(lbs),
+        check(lib.sr_shade_geometry(C.byref(sdf_net.desc),
+                                    C.byref(def_net.desc) if def_net is not None else None, _lbs_ref(lbs),
                                     _p(pts), _p(rays), _p(bi), _p(conds), condlen, P, _p(normals),
                                     _p(crays), _p(feat), int(nfeat), _p(dpos), _p(ok), _stream()),
               "shade_geometry")

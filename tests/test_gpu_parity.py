@@ -47,8 +47,9 @@ def test_minv3x3_forward_backward(cuda_dev):
         assert (inv.cpu().numpy()[~chk.cpu().numpy()] == 0).all()
         # property from the reference's own check script (FastMinv/check.py:18-19)
         good = chk & (torch.from_numpy(det).to(cuda_dev) > 1e-2)
-        err = (inv[good].double() @ ms.to(cuda_dev)[good].double() - torch.eye(3, device=cuda_dev, dtype=torch.float64)).norm(dim=(1, 2))
-        assert err.max().item() < 1e-3
+        if good.any():
+            err = (inv[good].double() @ ms.to(cuda_dev)[good].double() - torch.eye(3, device=cuda_dev, dtype=torch.float64)).norm(dim=(1, 2))
+            assert err.max().item() < 1e-3
         gr = torch.randn(n, 3, 3, generator=g)
         bo = FastMinv.Fast3x3Minv_backward(gr.to(cuda_dev), inv)
         ref = -(inv.transpose(1, 2) @ gr.to(cuda_dev) @ inv.transpose(1, 2))
@@ -77,8 +78,14 @@ def test_minv3x3_matches_reference_kernel(cuda_dev):
     torch.cuda.synchronize()
     assert torch.equal(ac, bc), "singularity mask identical to the reference kernel"
     det = torch.linalg.det(ms.double()).abs().view(-1, 1, 1)
-    # floating point: FMA contraction differs by an ulp between the two builds; compare adjugates
-    assert rel_err((a.double() * det).cpu().numpy(), (b.double() * det).cpu().numpy()) < 1e-6
+    # floating point: the 2x2 minors cancel, and FMA contraction differs between the two builds, so
+    # the two kernels agree to the conditioning of the minors, not to the last bit: both must be
+    # equally close to the float64 adjugate.
+    adj = (torch.linalg.inv(ms.double()) * torch.linalg.det(ms.double()).view(-1, 1, 1)).cpu().numpy()
+    sgn = torch.sign(torch.linalg.det(ms.double())).view(-1, 1, 1)
+    ea = rel_err((a.double() * det * sgn).cpu().numpy(), adj)
+    eb = rel_err((b.double() * det * sgn).cpu().numpy(), adj)
+    assert ea < 5e-5 and eb < 5e-5 and ea < 2 * eb + 1e-6
     gr = torch.randn_like(ms)
     assert rel_err(FastMinv.Fast3x3Minv_backward(gr, a).cpu().numpy(),
                    ref.Fast3x3Minv_backward(gr, b).cpu().numpy()) < 1e-6
@@ -418,6 +425,33 @@ def test_trace_vs_golden(cuda_dev):
     # empty ray set
     p0, c0 = utils.OptimizeSurfacePs(cam, rays[:0], start[:0].clone(), bi[:0], sdf, RATIO, comp, conds)
     assert p0.shape == (0, 3) and c0.shape == (0,)
+    # the two engines (reverse-mode sweeps = default, forward-mode tangents) agree with the
+    # reference and with each other; identity deformer (BASELINE config 1) through both
+    from selfreconcode_b200 import ops
+    sdf_only = sdf.fused_sdf_only()
+    dnet = comp.defs[0].fused(RATIO)
+    lbs = comp.defs[1].lbs_state()
+    lbs.set_pose(conds[1][0], conds[1][1])
+    res = {}
+    for mode in ("reverse", "forward"):
+        p, conv, cnt = ops.trace_surface_points(sdf_only, dnet, lbs, cam, rays, start, bi, conds[0], 5e-5,
+                                                float(t["athreshold"]), 3.05, 1.0, 10, return_counters=True,
+                                                mode=mode)
+        assert np.abs(p.cpu().numpy() - t["pts_train"]).max() < 7e-5
+        res[mode] = (p, cnt)
+        pi, ci = ops.trace_surface_points(sdf_only, None, None, cam, rays, start, bi, None, 5e-5, 0.5, 3.05,
+                                          1.0, 10, mode=mode)
+        res[mode + "_id"] = pi
+    assert torch.equal(res["reverse"][1], res["forward"][1]), "same active-set sizes per iteration"
+    assert (res["reverse"][0] - res["forward"][0]).abs().max().item() < 2e-6
+    assert (res["reverse_id"] - res["forward_id"]).abs().max().item() < 2e-6
+    # identity deformer against the oracle
+    from oracle import oracle as O
+    sp = [(a.cpu(), b.cpu(), c.cpu()) for a, b, c in sdf_params(sdf)]
+    po, co, _ = O.optimize_surface_ps(cam.cpu(), rays.cpu(), start.cpu(), bi.cpu(),
+                                      lambda q: O.sdf_forward(sp, q, 6, 1.0)[0], lambda q, b: q, 5e-5, 0.5,
+                                      3.05, 1.0, 10)
+    assert np.abs(res["reverse_id"].cpu().numpy() - po.numpy()).max() < 7e-5
 
 
 def test_seg3d_lossless_vs_golden_and_mc(cuda_dev):
