@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libselfrecon_b200.so")
+# SELFRECON_B200_LIB lets tuning scripts A/B differently-built libraries; default = in-tree build
+LIB_PATH = os.environ.get("SELFRECON_B200_LIB") or os.path.join(_HERE, "lib", "libselfrecon_b200.so")
 
 SR_OK = 0
 SR_EINVAL, SR_EUNSUPPORTED, SR_ECAPACITY = -1, -2, -3

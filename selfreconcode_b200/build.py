@@ -40,6 +40,28 @@ def lib_path():
     return os.path.join(LIBDIR, LIBNAME)
 
 
+def build_variant(tag, defines):
+    """Tuning helper: builds lib/variants/libselfrecon_b200_<tag>.so with extra -D defines."""
+    vdir = os.path.join(LIBDIR, "variants", tag)
+    os.makedirs(vdir, exist_ok=True)
+    nvcc = _nvcc()
+    objs = []
+    procs = []
+    for src in SOURCES:
+        o = os.path.join(vdir, src.replace(".cu", ".o"))
+        objs.append(o)
+        cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-c", os.path.join(CSRC, src), "-o", o]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(out.decode())
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    out = os.path.join(LIBDIR, "variants", "libselfrecon_b200_%s.so" % tag)
+    subprocess.check_call([nvcc, "-shared", "-o", out] + objs)
+    return out
+
+
 def build(force=False, verbose=True):
     os.makedirs(LIBDIR, exist_ok=True)
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]

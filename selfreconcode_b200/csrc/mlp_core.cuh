@@ -18,8 +18,13 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef SR_GEMM_UNROLL
+#define SR_GEMM_UNROLL 4
+#endif
+
 namespace srmlp {
 
+constexpr int kGemmUnroll = SR_GEMM_UNROLL;  // k-steps unrolled in the GEMM inner loop
 constexpr int kTileRows = 64;          // rows per CTA tile
 constexpr int kRowStride = 68;         // A_T row stride in floats (64 + 4 pad)
 constexpr int kMaxK = 512;             // max fan-in (padded)
@@ -220,7 +225,7 @@ __device__ __forceinline__ void layer_gemm(const Smem& s, Pipe& cp, Prod& prod, 
     // Unroll by 2 only: one (kk) body is 128 FFMA + 6 LDS = ~2.1 KB of SASS; the fully unrolled
     // 8-deep body (17 KB) overflowed the ~6 KB L0 instruction cache of the SM sub-partition and
     // ncu showed 0.65 "no_instruction" stalls per issued instruction (profiles/r01_sdf_kernel.md).
-#pragma unroll 2
+#pragma unroll kGemmUnroll
     for (int kk = 0; kk < kKT; ++kk) {
       const float4 a0 = *reinterpret_cast<const float4*>(ak + kk * kRowStride);
       const float4 a1 = *reinterpret_cast<const float4*>(ak + kk * kRowStride + 4);
