@@ -19,7 +19,13 @@
 #include "common.cuh"
 
 #ifndef SR_GEMM_UNROLL
-#define SR_GEMM_UNROLL 4
+#define SR_GEMM_UNROLL 8   // measured on B200: 2 / 4 / 8 within 2 %, 8 marginally best
+#endif
+#ifndef SR_WARPS
+#define SR_WARPS 8        // 8: 8x16 thread tile, <=255 regs;  16: 8x8 thread tile, <=128 regs
+#endif
+#ifndef SR_FAST_ACT
+#define SR_FAST_ACT 1     // MUFU-based softplus / sigmoid (abs. error < 3e-8 on activations)
 #endif
 
 namespace srmlp {
@@ -32,8 +38,11 @@ constexpr int kMaxN = 512;             // max fan-out (padded)
 constexpr int kKT = 8;                 // k rows per pipeline stage
 constexpr int kStages = 4;             // weight ring depth
 constexpr int kStageFloats = kKT * kMaxN;
-constexpr int kConsumerWarps = 8;
+constexpr int kConsumerWarps = SR_WARPS;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
+constexpr int kColSplit = kConsumerWarps / 8;      // warps sharing a row group split the column groups
+constexpr int kAccCols = 16 / kColSplit;           // accumulator columns per thread
+static_assert(kConsumerWarps == 8 || kConsumerWarps == 16, "8 or 16 warps");
 // No dedicated producer warp: a 9th warp would put 3 warps on one SM sub-partition and cap
 // every thread at 168 registers (spills in the 8x16 accumulator tile).  Thread 0 issues the
 // TMA refills itself, one stage behind its own consumption (see Prod).
@@ -191,9 +200,26 @@ __device__ __forceinline__ float softplus100(float z, float& deriv) {
   // torch.nn.Softplus(beta=100, threshold=20) and its autograd formula
   const float bz = z * 100.0f;
   if (bz > 20.0f) { deriv = 1.0f; return z; }
+#if SR_FAST_ACT
+  // MUFU.EX2 / MUFU.LG2 / fast divide: |error| <= ~3e-6 relative on e, i.e. < 3e-8 absolute on the
+  // activation (values are O(0.01..1)); the libm path costs ~3x the instructions per element
+  // and the epilogue was 15 % of all issued instructions (profiles/r01a_summary.md).
+  const float e = __expf(bz);
+  deriv = __fdividef(e, e + 1.0f);
+  return __logf(1.0f + e) * 0.01f;
+#else
   const float e = expf(bz);
   deriv = e / (e + 1.0f);
   return log1pf(e) / 100.0f;
+#endif
+}
+// x / np.sqrt(2) of the skip connection (model/network.py:88-89)
+__device__ __forceinline__ float div_sqrt2(float x) {
+#if SR_FAST_ACT
+  return x * 0.70710678118654752440f;
+#else
+  return __fdiv_rn(x, 1.41421356237309504880f);
+#endif
 }
 __device__ __forceinline__ float apply_act(int act, float z, float& deriv) {
   switch (act) {
@@ -205,40 +231,45 @@ __device__ __forceinline__ float apply_act(int act, float z, float& deriv) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// One layer: acc[8][4G] = A_T[0:kpad][rows]^T * W_T[0:kpad][cols]
-//   thread (warp w, lane l) owns rows 8w..8w+7 and cols { g*128 + 4*l + i }.
+// One layer: acc = A_T[0:kpad][rows]^T * W_T[0:kpad][cols]
+//   8 warps : thread (warp w, lane l) owns rows 8w..8w+7 and cols { g*128 + 4*l + i }, g < 4.
 // ---------------------------------------------------------------------------------------------
-template <int G>
+// With 16 warps two warps share a row group and take alternate 128-column groups:
+//   warp w: rows 8*(w%8).., groups { g*kColSplit + w/8 }.
+template <int GP>
 __device__ __forceinline__ void layer_gemm(const Smem& s, Pipe& cp, Prod& prod, int kpad,
-                                           int npad, float (&acc)[8][16]) {
+                                           int npad, float (&acc)[8][kAccCols]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rg = warp & 7, ch = warp >> 3;
+  const int ngroups = npad >> 7;
 #pragma unroll
   for (int r = 0; r < 8; ++r)
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc[r][c] = 0.0f;
-  const float* arow = s.at + 8 * warp;
+    for (int c = 0; c < kAccCols; ++c) acc[r][c] = 0.0f;
+  const float* arow = s.at + 8 * rg;
   const int nslices = kpad / kKT;
   for (int sl = 0; sl < nslices; ++sl) {
     sr_mbar_wait(&s.full[cp.slot], cp.phase);
-    const float* wst = s.wring + (size_t)cp.slot * kStageFloats + 4 * lane;
+    const float* wst = s.wring + (size_t)cp.slot * kStageFloats + 4 * lane + ch * 128;
     const float* ak = arow + (size_t)sl * kKT * kRowStride;
-    // Unroll by 2 only: one (kk) body is 128 FFMA + 6 LDS = ~2.1 KB of SASS; the fully unrolled
-    // 8-deep body (17 KB) overflowed the ~6 KB L0 instruction cache of the SM sub-partition and
-    // ncu showed 0.65 "no_instruction" stalls per issued instruction (profiles/r01_sdf_kernel.md).
+    // (The "no_instruction" stalls seen in profiles/r01a_summary.md come from the epilogue code,
+    // not from this loop: unrolling 2 / 4 / 8 k-steps measured within 2 % of each other.)
 #pragma unroll kGemmUnroll
     for (int kk = 0; kk < kKT; ++kk) {
       const float4 a0 = *reinterpret_cast<const float4*>(ak + kk * kRowStride);
       const float4 a1 = *reinterpret_cast<const float4*>(ak + kk * kRowStride + 4);
       const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const float4 w4 = *reinterpret_cast<const float4*>(wst + kk * npad + g * 128);
+      for (int g = 0; g < GP; ++g) {
+        if (kColSplit == 1 || g * kColSplit + ch < ngroups) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wst + kk * npad + g * kColSplit * 128);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          acc[r][4 * g + 0] = fmaf(a[r], w4.x, acc[r][4 * g + 0]);
-          acc[r][4 * g + 1] = fmaf(a[r], w4.y, acc[r][4 * g + 1]);
-          acc[r][4 * g + 2] = fmaf(a[r], w4.z, acc[r][4 * g + 2]);
-          acc[r][4 * g + 3] = fmaf(a[r], w4.w, acc[r][4 * g + 3]);
+          for (int r = 0; r < 8; ++r) {
+            acc[r][4 * g + 0] = fmaf(a[r], w4.x, acc[r][4 * g + 0]);
+            acc[r][4 * g + 1] = fmaf(a[r], w4.y, acc[r][4 * g + 1]);
+            acc[r][4 * g + 2] = fmaf(a[r], w4.z, acc[r][4 * g + 2]);
+            acc[r][4 * g + 3] = fmaf(a[r], w4.w, acc[r][4 * g + 3]);
+          }
         }
       }
     }
@@ -262,22 +293,22 @@ struct LastOut {
 };
 constexpr size_t kDstashLayerFloats = (size_t)kMaxN * kTileRows;
 
-template <int G, int T>
+template <int GP, int T>
 __device__ __forceinline__ void layer_epilogue(const Smem& s, const sr_mlp_layer& L, int layer,
                                                bool last, bool next_skip, int next_kpad, int d_in,
-                                               const LastOut& lo, float (&acc)[8][16]) {
+                                               const LastOut& lo, float (&acc)[8][kAccCols]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rg = warp & 7, ch = warp >> 3;
   constexpr int CH = T + 1;
   constexpr int PPT = 8 / CH;  // points per thread
-  const float inv_div = 1.41421356237309504880f;  // np.sqrt(2) rounded to fp32
   // (1) every warp must be done reading A_T before anyone overwrites it
   consumer_sync();
 #pragma unroll
-  for (int g = 0; g < G; ++g) {
+  for (int g = 0; g < GP; ++g) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int c = 4 * g + i;
-      const int col = g * 128 + 4 * lane + i;
+      const int col = (g * kColSplit + ch) * 128 + 4 * lane + i;
       if (col < L.n) {
         const float b = __ldg(L.bias + col);
         float o[8];
@@ -292,27 +323,27 @@ __device__ __forceinline__ void layer_epilogue(const Smem& s, const sr_mlp_layer
           for (int t = 1; t < CH; ++t) o[p * CH + t] = d * acc[p * CH + t][c];
         }
         if (T == 0 && !last && lo.dstash != nullptr) {
-          float* dd = lo.dstash + (size_t)layer * kDstashLayerFloats + (size_t)col * kTileRows + 8 * warp;
+          float* dd = lo.dstash + (size_t)layer * kDstashLayerFloats + (size_t)col * kTileRows + 8 * rg;
           *reinterpret_cast<float4*>(dd) = make_float4(dv[0], dv[1], dv[2], dv[3]);
           *reinterpret_cast<float4*>(dd + 4) = make_float4(dv[4], dv[5], dv[6], dv[7]);
         }
         if (!last) {
           if (next_skip) {
 #pragma unroll
-            for (int r = 0; r < 8; ++r) o[r] = __fdiv_rn(o[r], inv_div);
+            for (int r = 0; r < 8; ++r) o[r] = div_sqrt2(o[r]);
           }
-          float* dst = s.at + (size_t)col * kRowStride + 8 * warp;
+          float* dst = s.at + (size_t)col * kRowStride + 8 * rg;
           *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
           *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
         } else {
           if (col < 8) {
 #pragma unroll
-            for (int r = 0; r < 8; ++r) s.res[(8 * warp + r) * 8 + col] = o[r];
+            for (int r = 0; r < 8; ++r) s.res[(8 * rg + r) * 8 + col] = o[r];
           }
           if (lo.feat != nullptr && col >= 1 && col <= lo.nfeat) {
 #pragma unroll
             for (int p = 0; p < PPT; ++p) {
-              const int gp = lo.row_pt[(8 * warp) / CH + p];
+              const int gp = lo.row_pt[(8 * rg) / CH + p];
               if (gp >= 0) lo.feat[(size_t)gp * lo.nfeat + (col - 1)] = o[p * CH];
             }
           }
@@ -321,7 +352,7 @@ __device__ __forceinline__ void layer_epilogue(const Smem& s, const sr_mlp_layer
         // zero the k-padding rows the next layer will multiply by zero weights
         const int lim = next_skip ? 0 : next_kpad;  // (skip case handled below)
         if (col < lim) {
-          float* dst = s.at + (size_t)col * kRowStride + 8 * warp;
+          float* dst = s.at + (size_t)col * kRowStride + 8 * rg;
           *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
           *reinterpret_cast<float4*>(dst + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -335,8 +366,7 @@ __device__ __forceinline__ void layer_epilogue(const Smem& s, const sr_mlp_layer
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (kk < d_in) {
         v = *reinterpret_cast<const float4*>(s.stash + (size_t)kk * kRowStride + r4);
-        v.x = __fdiv_rn(v.x, inv_div); v.y = __fdiv_rn(v.y, inv_div);
-        v.z = __fdiv_rn(v.z, inv_div); v.w = __fdiv_rn(v.w, inv_div);
+        v.x = div_sqrt2(v.x); v.y = div_sqrt2(v.y); v.z = div_sqrt2(v.z); v.w = div_sqrt2(v.w);
       }
       *reinterpret_cast<float4*>(s.at + (size_t)(L.n + kk) * kRowStride + r4) = v;
     }
@@ -350,29 +380,40 @@ __device__ __forceinline__ void layer_epilogue(const Smem& s, const sr_mlp_layer
 template <int T>
 __device__ __forceinline__ void run_net(const sr_mlp_desc& net, const Smem& s, Pipe& cp,
                                         Prod& prod, const LastOut& lo) {
-  float acc[8][16];
+  float acc[8][kAccCols];
   for (int l = 0; l < net.n_layers; ++l) {
     const sr_mlp_layer& L = net.layer[l];
     const bool last = (l == net.n_layers - 1);
     const bool next_skip = !last && net.layer[l + 1].skip != 0;
     const int next_kpad = last ? 0 : net.layer[l + 1].kpad;
-    switch (L.npad >> 7) {
-      case 1:
+    const int gp = ((L.npad >> 7) + kColSplit - 1) / kColSplit;  // column groups per thread
+    if (kColSplit == 2) {
+      if (gp == 1) {
         layer_gemm<1>(s, cp, prod, L.kpad, L.npad, acc);
         layer_epilogue<1, T>(s, L, l, last, next_skip, next_kpad, net.d_in, lo, acc);
-        break;
-      case 2:
-        layer_gemm<2>(s, cp, prod, L.kpad, L.npad, acc);
-        layer_epilogue<2, T>(s, L, l, last, next_skip, next_kpad, net.d_in, lo, acc);
-        break;
-      case 3:
-        layer_gemm<3>(s, cp, prod, L.kpad, L.npad, acc);
-        layer_epilogue<3, T>(s, L, l, last, next_skip, next_kpad, net.d_in, lo, acc);
-        break;
-      default:
-        layer_gemm<4>(s, cp, prod, L.kpad, L.npad, acc);
-        layer_epilogue<4, T>(s, L, l, last, next_skip, next_kpad, net.d_in, lo, acc);
-        break;
+      } else {
+        layer_gemm<(kColSplit == 2 ? 2 : 1)>(s, cp, prod, L.kpad, L.npad, acc);
+        layer_epilogue<(kColSplit == 2 ? 2 : 1), T>(s, L, l, last, next_skip, next_kpad, net.d_in, lo, acc);
+      }
+    } else {
+      switch (gp) {
+        case 1:
+          layer_gemm<1>(s, cp, prod, L.kpad, L.npad, acc);
+          layer_epilogue<1, T>(s, L, l, last, next_skip, next_kpad, net.d_in, lo, acc);
+          break;
+        case 2:
+          layer_gemm<(kColSplit == 1 ? 2 : 1)>(s, cp, prod, L.kpad, L.npad, acc);
+          layer_epilogue<(kColSplit == 1 ? 2 : 1), T>(s, L, l, last, next_skip, next_kpad, net.d_in, lo, acc);
+          break;
+        case 3:
+          layer_gemm<(kColSplit == 1 ? 3 : 1)>(s, cp, prod, L.kpad, L.npad, acc);
+          layer_epilogue<(kColSplit == 1 ? 3 : 1), T>(s, L, l, last, next_skip, next_kpad, net.d_in, lo, acc);
+          break;
+        default:
+          layer_gemm<(kColSplit == 1 ? 4 : 1)>(s, cp, prod, L.kpad, L.npad, acc);
+          layer_epilogue<(kColSplit == 1 ? 4 : 1), T>(s, L, l, last, next_skip, next_kpad, net.d_in, lo, acc);
+          break;
+      }
     }
   }
 }
@@ -384,34 +425,36 @@ __device__ __forceinline__ void run_net(const sr_mlp_desc& net, const Smem& s, P
 // Backward GEMM of layer l: g_in[rows x fan_in] = delta_l[rows x fan_out] * W_l, streamed from the
 // un-transposed padded copy `wb`; delta_{l-1} = g_in * act'_{l-1} (and the /sqrt(2) of a skip).
 // ---------------------------------------------------------------------------------------------
-template <int G>
+template <int GP>
 __device__ __forceinline__ void bwd_epilogue(const Smem& s, const sr_mlp_desc& net, int l,
-                                             const float* dstash, float (&acc)[8][16]) {
+                                             const float* dstash, float (&acc)[8][kAccCols]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rg = warp & 7, ch = warp >> 3;
   const sr_mlp_layer& L = net.layer[l];
-  const float inv_div = 1.41421356237309504880f;
   const bool skip = L.skip != 0;
   const int n_prev = l > 0 ? net.layer[l - 1].n : 0;         // width of the previous layer's output
   const int next_k = l > 0 ? bwd_kpad(net.layer[l - 1]) : 0;  // K of the next backward GEMM
   consumer_sync();
+  const int ngroups = bwd_npad(L) >> 7;
 #pragma unroll
-  for (int g = 0; g < G; ++g) {
+  for (int g = 0; g < GP; ++g) {
+    if (kColSplit == 2 && g * kColSplit + ch >= ngroups) continue;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int c = 4 * g + i;
-      const int col = g * 128 + 4 * lane + i;
+      const int col = (g * kColSplit + ch) * 128 + 4 * lane + i;
       float o[8];
 #pragma unroll
       for (int r = 0; r < 8; ++r) o[r] = acc[r][c];
       if (skip) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) o[r] = __fdiv_rn(o[r], inv_div);
+        for (int r = 0; r < 8; ++r) o[r] = div_sqrt2(o[r]);
       }
       if (l == 0) {
         if (col < L.k) {
-          float* dst = s.at + (size_t)col * kRowStride + 8 * warp;
+          float* dst = s.at + (size_t)col * kRowStride + 8 * rg;
           if (col < kStashMax) {  // add the gradient that arrived through the skip connection
-            const float* sg = s.stash + (size_t)col * kRowStride + 8 * warp;
+            const float* sg = s.stash + (size_t)col * kRowStride + 8 * rg;
 #pragma unroll
             for (int r = 0; r < 8; ++r) o[r] += sg[r];
           }
@@ -419,20 +462,20 @@ __device__ __forceinline__ void bwd_epilogue(const Smem& s, const sr_mlp_desc& n
           *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
         }
       } else if (col < n_prev) {
-        const float* dd = dstash + (size_t)(l - 1) * kDstashLayerFloats + (size_t)col * kTileRows + 8 * warp;
+        const float* dd = dstash + (size_t)(l - 1) * kDstashLayerFloats + (size_t)col * kTileRows + 8 * rg;
         const float4 d0 = *reinterpret_cast<const float4*>(dd);
         const float4 d1 = *reinterpret_cast<const float4*>(dd + 4);
-        float* dst = s.at + (size_t)col * kRowStride + 8 * warp;
+        float* dst = s.at + (size_t)col * kRowStride + 8 * rg;
         *reinterpret_cast<float4*>(dst) = make_float4(o[0] * d0.x, o[1] * d0.y, o[2] * d0.z, o[3] * d0.w);
         *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4] * d1.x, o[5] * d1.y, o[6] * d1.z, o[7] * d1.w);
       } else {
         if (skip && col < n_prev + net.d_in && col - n_prev < kStashMax) {
-          float* sg = s.stash + (size_t)(col - n_prev) * kRowStride + 8 * warp;
+          float* sg = s.stash + (size_t)(col - n_prev) * kRowStride + 8 * rg;
           *reinterpret_cast<float4*>(sg) = make_float4(o[0], o[1], o[2], o[3]);
           *reinterpret_cast<float4*>(sg + 4) = make_float4(o[4], o[5], o[6], o[7]);
         }
         if (col < next_k) {  // k-padding of the next backward GEMM
-          float* dst = s.at + (size_t)col * kRowStride + 8 * warp;
+          float* dst = s.at + (size_t)col * kRowStride + 8 * rg;
           *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
           *reinterpret_cast<float4*>(dst + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -452,15 +495,21 @@ __device__ __forceinline__ void bwd_clear_stash(const Smem& s) {
 
 __device__ __forceinline__ void run_net_bwd(const sr_mlp_desc& net, const Smem& s, Pipe& cp,
                                             Prod& prod, const float* dstash) {
-  float acc[8][16];
+  float acc[8][kAccCols];
   for (int l = net.n_layers - 1; l >= 0; --l) {
     const sr_mlp_layer& L = net.layer[l];
     const int kp = bwd_kpad(L), np = bwd_npad(L);
-    switch (np >> 7) {
-      case 1: layer_gemm<1>(s, cp, prod, kp, np, acc); bwd_epilogue<1>(s, net, l, dstash, acc); break;
-      case 2: layer_gemm<2>(s, cp, prod, kp, np, acc); bwd_epilogue<2>(s, net, l, dstash, acc); break;
-      case 3: layer_gemm<3>(s, cp, prod, kp, np, acc); bwd_epilogue<3>(s, net, l, dstash, acc); break;
-      default: layer_gemm<4>(s, cp, prod, kp, np, acc); bwd_epilogue<4>(s, net, l, dstash, acc); break;
+    const int gp = ((np >> 7) + kColSplit - 1) / kColSplit;
+    if (kColSplit == 2) {
+      if (gp == 1) { layer_gemm<1>(s, cp, prod, kp, np, acc); bwd_epilogue<1>(s, net, l, dstash, acc); }
+      else { layer_gemm<(kColSplit == 2 ? 2 : 1)>(s, cp, prod, kp, np, acc); bwd_epilogue<(kColSplit == 2 ? 2 : 1)>(s, net, l, dstash, acc); }
+    } else {
+      switch (gp) {
+        case 1: layer_gemm<1>(s, cp, prod, kp, np, acc); bwd_epilogue<1>(s, net, l, dstash, acc); break;
+        case 2: layer_gemm<(kColSplit == 1 ? 2 : 1)>(s, cp, prod, kp, np, acc); bwd_epilogue<(kColSplit == 1 ? 2 : 1)>(s, net, l, dstash, acc); break;
+        case 3: layer_gemm<(kColSplit == 1 ? 3 : 1)>(s, cp, prod, kp, np, acc); bwd_epilogue<(kColSplit == 1 ? 3 : 1)>(s, net, l, dstash, acc); break;
+        default: layer_gemm<(kColSplit == 1 ? 4 : 1)>(s, cp, prod, kp, np, acc); bwd_epilogue<(kColSplit == 1 ? 4 : 1)>(s, net, l, dstash, acc); break;
+      }
     }
   }
 }

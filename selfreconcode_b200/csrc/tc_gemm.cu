@@ -1,0 +1,398 @@
+// Tensor-core engine for the dense layers: fp32-faithful BF16x3 split GEMM on tcgen05
+// (SURVEY.md section 7 "hard parts": the ray finder tests |f| < 5e-5, single-pass BF16/TF32
+// does not hold that; x = b1 + b2 + b3 with three bf16 terms carries 24 mantissa bits and
+//   x*w ~= b1w1 + b1w2 + b2w1 + b2w2 + b1w3 + b3w1      (dropped terms <= 2^-24 relative)
+// costs six bf16 MMAs, i.e. 1/6 of the bf16 tensor peak, accumulated in fp32 in TMEM).
+//
+// One launch = one layer  C[M x N] = act(A[M x K] * W^T + b)  over all row tiles:
+//   * operands live in global memory already in the canonical (no-swizzle, K-major) shared
+//     memory layout of the UMMA descriptors -- 128-byte core matrices (8 rows x 8 bf16), tiles
+//     of 128 (or 256) rows x 32 k, the three split planes of a tile contiguous -- so ONE TMA bulk
+//     copy (cp.async.bulk + mbarrier) per operand per stage lands a ready-to-use tile and no
+//     tensor map is needed.  The previous layer's epilogue writes its output directly in that
+//     layout (activations stay L2-resident between layers for the batch sizes used here);
+//   * warp-specialised, persistent CTAs: warp 0 = TMA producer, warp 1 = single-thread
+//     tcgen05.mma issuer (+ TMEM alloc), warps 2-5 = epilogue (tcgen05.ld -> bias, activation,
+//     forward-mode tangent scaling, re-split to bf16x3, tiled store);
+//   * 3-stage shared-memory ring (72 KB per stage), two 256-column fp32 accumulators in TMEM so
+//     the epilogue of tile i overlaps the MMAs of tile i+1.
+// The FFMA engine (mlp_kernels.cu) stays the accuracy reference; tests compare both.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace sr_tc {
+
+constexpr int BM = 128, BN = 256, BK = 32, STAGES = 3;
+constexpr int kThreads = 192;
+constexpr int A_PLANE = BM * BK;          // elements
+constexpr int W_PLANE = BN * BK;
+constexpr int A_STAGE = 3 * A_PLANE;      // 12288 bf16 = 24 KB
+constexpr int W_STAGE = 3 * W_PLANE;      // 24576 bf16 = 48 KB
+constexpr uint32_t A_STAGE_BYTES = A_STAGE * 2, W_STAGE_BYTES = W_STAGE * 2;
+constexpr size_t kSmem = (size_t)STAGES * (A_STAGE_BYTES + W_STAGE_BYTES) + 256;
+
+// ---- tiled ("pre-swizzled") global layouts ----------------------------------------------------
+// A: [row tile mt][k chunk kc][plane p][k8 (4)][row group (16)][row (8)][elem (8)]
+// W: [col tile nt][k chunk kc][plane p][k8 (4)][row group (32)][row (8)][elem (8)]
+__host__ __device__ inline size_t a_tile_off(long long mt, int kc, int KC, int p) {
+  return (((size_t)mt * KC + kc) * 3 + p) * A_PLANE;
+}
+__host__ __device__ inline size_t w_tile_off(int nt, int kc, int KC, int p) {
+  return (((size_t)nt * KC + kc) * 3 + p) * W_PLANE;
+}
+__device__ __forceinline__ int in_tile_off(int rows_per_tile, int r, int k) {
+  return (k >> 3) * (rows_per_tile * 8) + (r >> 3) * 64 + (r & 7) * 8 + (k & 7);
+}
+
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& b1, __nv_bfloat16& b2, __nv_bfloat16& b3) {
+  b1 = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(b1);
+  b2 = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(b2);
+  b3 = __float2bfloat16_rn(r2);
+}
+
+// ---- tcgen05 wrappers ------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // cute::UMMA::SmemDescriptor: start[0,14) lbo[16,30) sbo[32,46) version[46,48)=1, swizzle none
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=256
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                            ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   sr_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct LayerArgs {
+  const __nv_bfloat16* A;   // tiled activations  [MT][KC][3][128x32]
+  const __nv_bfloat16* W;   // tiled weights      [NT][KC][3][256x32]
+  const float* bias;        // [NT*256]
+  long long M;              // valid rows
+  int MT, NT, KC;           // row tiles, col tiles, k chunks (K = 32*KC)
+  int n;                    // valid output columns
+  int act;                  // SR_ACT_*
+  int ch;                   // rows per point: 1 (value only) or 4 (value + 3 tangents)
+  // outputs (either may be null)
+  __nv_bfloat16* A_next;    // tiled, KCn chunks: activations for the next layer
+  int KCn;
+  float scale;              // 1, or 1/sqrt(2) when the next layer is the skip layer
+  const float* skip_src;    // fp32 [M][skip_ld] embedded input appended after column n (or null)
+  int skip_n, skip_ld;
+  float* out;               // fp32 row-major [M][out_ld] (last layer), columns [0, n)
+  int out_ld;
+  float* dstash;            // fp32 row-major [M][NT*256] act'(z) of value rows (reverse mode) or null
+};
+
+__device__ __forceinline__ float act_fn(int act, float z, float& d) {
+  if (act == SR_ACT_SOFTPLUS100) {
+    const float bz = z * 100.0f;
+    if (bz > 20.0f) { d = 1.0f; return z; }
+    const float e = __expf(bz);
+    d = __fdividef(e, e + 1.0f);
+    return __logf(1.0f + e) * 0.01f;
+  }
+  if (act == SR_ACT_RELU) { d = z > 0.f ? 1.f : 0.f; return z > 0.f ? z : 0.f; }
+  if (act == SR_ACT_TANH) { const float t = tanhf(z); d = 1.f - t * t; return t; }
+  d = 1.f;
+  return z;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(const __grid_constant__ LayerArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem);
+  __nv_bfloat16* sW = reinterpret_cast<__nv_bfloat16*>(smem + (size_t)STAGES * A_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * (A_STAGE_BYTES + W_STAGE_BYTES));
+  uint64_t* full = bars;                 // [STAGES]
+  uint64_t* empty = bars + STAGES;       // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty = tfull + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { sr_mbar_init(&full[i], 1); sr_mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { sr_mbar_init(&tfull[i], 1); sr_mbar_init(&tempty[i], 4); }
+    sr_fence_barrier_init();
+  }
+  if (warp == 1) {  // TMEM: all 512 columns (two 256-column accumulators)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     sr_smem_u32(tmem_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const long long ntiles = (long long)a.MT * a.NT;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const long long mt = t / a.NT;
+        const int nt = (int)(t % a.NT);
+        for (int kc = 0; kc < a.KC; ++kc) {
+          sr_mbar_wait(&empty[slot], phase ^ 1u);
+          sr_mbar_arrive_expect_tx(&full[slot], A_STAGE_BYTES + W_STAGE_BYTES);
+          sr_bulk_g2s(sA + (size_t)slot * A_STAGE, a.A + a_tile_off(mt, kc, a.KC, 0), A_STAGE_BYTES, &full[slot]);
+          sr_bulk_g2s(sW + (size_t)slot * W_STAGE, a.W + w_tile_off(nt, kc, a.KC, 0), W_STAGE_BYTES, &full[slot]);
+          if (++slot == STAGES) { slot = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      int buf = 0;
+      uint32_t bphase = 0;
+      // plane pairs, smallest contributions first
+      const int pa[6] = {0, 2, 1, 0, 1, 0};
+      const int pw[6] = {2, 0, 1, 1, 0, 0};
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        sr_mbar_wait(&tempty[buf], bphase ^ 1u);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)buf * BN;
+        uint32_t accumulate = 0;
+        for (int kc = 0; kc < a.KC; ++kc) {
+          sr_mbar_wait(&full[slot], phase);
+          tc_fence_after();
+          const uint32_t abase = sr_smem_u32(sA + (size_t)slot * A_STAGE);
+          const uint32_t wbase = sr_smem_u32(sW + (size_t)slot * W_STAGE);
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+#pragma unroll
+            for (int j = 0; j < BK / 16; ++j) {
+              // K = 16 per MMA = two 8-wide core matrices: advance two LBO steps per j
+              const uint64_t ad = make_desc(abase + pa[q] * (A_PLANE * 2) + j * 2 * (BM * 16), BM * 16, 128);
+              const uint64_t bd = make_desc(wbase + pw[q] * (W_PLANE * 2) + j * 2 * (BN * 16), BN * 16, 128);
+              mma_bf16(tmem_d, ad, bd, accumulate);
+              accumulate = 1;
+            }
+          }
+          mma_commit(&empty[slot]);  // frees the smem stage when these MMAs have read it
+          if (++slot == STAGES) { slot = 0; phase ^= 1u; }
+        }
+        mma_commit(&tfull[buf]);     // accumulator complete
+        if (++buf == 2) { buf = 0; bphase ^= 1u; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int row_in_tile = q * 32 + lane;
+    int buf = 0;
+    uint32_t bphase = 0;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const long long mt = t / a.NT;
+      const int nt = (int)(t % a.NT);
+      const long long row = mt * BM + row_in_tile;
+      sr_mbar_wait(&tfull[buf], bphase);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * BN;
+      const bool is_val = (a.ch == 1) || ((lane & 3) == 0);
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        uint32_t v[32];
+        tmem_ld32(taddr0 + chunk * 32, v);
+        const int c0 = nt * BN + chunk * 32;
+        float o[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int c = c0 + j;
+          const float acc = __uint_as_float(v[j]);
+          float d = 1.f, val;
+          const float z = acc + (is_val ? __ldg(a.bias + c) : 0.f);
+          if (is_val) val = act_fn(a.act, z, d);
+          else val = 0.f;
+          if (a.ch == 4) {
+            const float dv = __shfl_sync(0xffffffffu, d, lane & ~3);  // act'(z) of the value row
+            if (!is_val) val = dv * acc;
+          }
+          if (a.dstash != nullptr && is_val && row < a.M) a.dstash[(size_t)row * ((size_t)a.NT * BN) + c] = d;
+          val *= a.scale;
+          if (c >= a.n) {
+            val = 0.f;
+            if (a.skip_src != nullptr && c < a.n + a.skip_n && row < a.M)
+              val = a.skip_src[(size_t)row * a.skip_ld + (c - a.n)] * a.scale;
+          }
+          o[j] = val;
+        }
+        if (a.A_next != nullptr) {
+          const int kcn = c0 >> 5;  // next layer's k chunk
+          if (kcn < a.KCn) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              __align__(16) __nv_bfloat16 p1[8], p2[8], p3[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) split3(o[g * 8 + e], p1[e], p2[e], p3[e]);
+              const size_t off = (size_t)g * (BM * 8) + (size_t)(row_in_tile >> 3) * 64 + (row_in_tile & 7) * 8;
+              *reinterpret_cast<uint4*>(a.A_next + a_tile_off(mt, kcn, a.KCn, 0) + off) = *reinterpret_cast<uint4*>(p1);
+              *reinterpret_cast<uint4*>(a.A_next + a_tile_off(mt, kcn, a.KCn, 1) + off) = *reinterpret_cast<uint4*>(p2);
+              *reinterpret_cast<uint4*>(a.A_next + a_tile_off(mt, kcn, a.KCn, 2) + off) = *reinterpret_cast<uint4*>(p3);
+            }
+          }
+        }
+        if (a.out != nullptr && row < a.M) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < a.n) a.out[(size_t)row * a.out_ld + c0 + j] = o[j];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) sr_mbar_arrive(&tempty[buf]);
+      if (++buf == 2) { buf = 0; bphase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---- packing kernels -------------------------------------------------------------------------
+// fp32 row-major [M][K] (ld) -> tiled bf16x3 activations with KC = ceil(Kpad/32) chunks
+__global__ void pack_rows_kernel(const float* __restrict__ src, long long M, int K, int ld,
+                                 __nv_bfloat16* __restrict__ dst, int KC, long long MT) {
+  const long long total = MT * BM * (long long)KC * 4;  // one thread per (row, k8 group)
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx % BM);
+    const long long rest = idx / BM;
+    const int g = (int)(rest % (KC * 4));
+    const long long mt = rest / (KC * 4);
+    const long long row = mt * BM + r;
+    const int kc = g >> 2, k8 = g & 3;
+    __align__(16) __nv_bfloat16 p1[8], p2[8], p3[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = kc * 32 + k8 * 8 + e;
+      const float x = (row < M && k < K) ? src[(size_t)row * ld + k] : 0.f;
+      split3(x, p1[e], p2[e], p3[e]);
+    }
+    const size_t off = (size_t)k8 * (BM * 8) + (size_t)(r >> 3) * 64 + (r & 7) * 8;
+    *reinterpret_cast<uint4*>(dst + a_tile_off(mt, kc, KC, 0) + off) = *reinterpret_cast<uint4*>(p1);
+    *reinterpret_cast<uint4*>(dst + a_tile_off(mt, kc, KC, 1) + off) = *reinterpret_cast<uint4*>(p2);
+    *reinterpret_cast<uint4*>(dst + a_tile_off(mt, kc, KC, 2) + off) = *reinterpret_cast<uint4*>(p3);
+  }
+}
+
+// effective weights, fp32 row-major [N][K] (ld) -> tiled bf16x3 [NT][KC][3][256x32]
+__global__ void pack_weights_kernel(const float* __restrict__ w, int N, int K, int ld,
+                                    __nv_bfloat16* __restrict__ dst, int NT, int KC) {
+  const long long total = (long long)NT * BN * KC * 4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx % BN);
+    const long long rest = idx / BN;
+    const int g = (int)(rest % (KC * 4));
+    const int nt = (int)(rest / (KC * 4));
+    const int n = nt * BN + r;
+    const int kc = g >> 2, k8 = g & 3;
+    __align__(16) __nv_bfloat16 p1[8], p2[8], p3[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = kc * 32 + k8 * 8 + e;
+      const float x = (n < N && k < K) ? w[(size_t)n * ld + k] : 0.f;
+      split3(x, p1[e], p2[e], p3[e]);
+    }
+    const size_t off = (size_t)k8 * (BN * 8) + (size_t)(r >> 3) * 64 + (r & 7) * 8;
+    *reinterpret_cast<uint4*>(dst + w_tile_off(nt, kc, KC, 0) + off) = *reinterpret_cast<uint4*>(p1);
+    *reinterpret_cast<uint4*>(dst + w_tile_off(nt, kc, KC, 1) + off) = *reinterpret_cast<uint4*>(p2);
+    *reinterpret_cast<uint4*>(dst + w_tile_off(nt, kc, KC, 2) + off) = *reinterpret_cast<uint4*>(p3);
+  }
+}
+
+}  // namespace sr_tc
+
+extern "C" {
+
+int64_t sr_tc_act_bytes(int64_t M, int K) {
+  const int64_t MT = (M + sr_tc::BM - 1) / sr_tc::BM, KC = (K + 31) / 32;
+  return MT * KC * 3 * sr_tc::A_PLANE * 2;
+}
+int64_t sr_tc_weight_bytes(int N, int K) {
+  const int64_t NT = (N + sr_tc::BN - 1) / sr_tc::BN, KC = (K + 31) / 32;
+  return NT * KC * 3 * sr_tc::W_PLANE * 2;
+}
+
+int sr_tc_pack_rows(const float* src, int64_t M, int K, int ld, void* dst, cudaStream_t s) {
+  if (!src || !dst || M <= 0 || K <= 0 || ld < K) return SR_EINVAL;
+  const long long MT = (M + sr_tc::BM - 1) / sr_tc::BM;
+  const int KC = (K + 31) / 32;
+  const long long total = MT * sr_tc::BM * KC * 4;
+  sr_tc::pack_rows_kernel<<<sr_grid_for(total, 256, 8), 256, 0, s>>>(src, M, K, ld, (__nv_bfloat16*)dst, KC, MT);
+  return sr_launch_status();
+}
+
+int sr_tc_pack_weights(const float* w, int N, int K, int ld, void* dst, cudaStream_t s) {
+  if (!w || !dst || N <= 0 || K <= 0 || ld < K) return SR_EINVAL;
+  const int NT = (N + sr_tc::BN - 1) / sr_tc::BN, KC = (K + 31) / 32;
+  const long long total = (long long)NT * sr_tc::BN * KC * 4;
+  sr_tc::pack_weights_kernel<<<sr_grid_for(total, 256, 8), 256, 0, s>>>(w, N, K, ld, (__nv_bfloat16*)dst, NT, KC);
+  return sr_launch_status();
+}
+
+int sr_tc_linear(const void* A, const void* W, const float* bias, int64_t M, int N, int K, int n_valid,
+                 int act, int ch, void* A_next, int K_next, float scale, const float* skip_src,
+                 int skip_n, int skip_ld, float* out, int out_ld, float* dstash, cudaStream_t s) {
+  using namespace sr_tc;
+  if (!A || !W || !bias || M <= 0 || N <= 0 || K <= 0 || (ch != 1 && ch != 4)) return SR_EINVAL;
+  if (!A_next && !out) return SR_EINVAL;
+  LayerArgs a;
+  a.A = (const __nv_bfloat16*)A; a.W = (const __nv_bfloat16*)W; a.bias = bias; a.M = M;
+  a.MT = (int)((M + BM - 1) / BM); a.NT = (N + BN - 1) / BN; a.KC = (K + 31) / 32;
+  a.n = n_valid; a.act = act; a.ch = ch;
+  a.A_next = (__nv_bfloat16*)A_next; a.KCn = A_next ? (K_next + 31) / 32 : 0;
+  a.scale = scale; a.skip_src = skip_src; a.skip_n = skip_n; a.skip_ld = skip_ld;
+  a.out = out; a.out_ld = out_ld; a.dstash = dstash;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const long long ntiles = (long long)a.MT * a.NT;
+  const int grid = (int)(ntiles < SR_NUM_SMS_B200 ? ntiles : SR_NUM_SMS_B200);
+  tc_layer_kernel<<<grid, kThreads, kSmem, s>>>(a);
+  return sr_launch_status();
+}
+}
