@@ -110,8 +110,9 @@ def make_engine(sc, dev):
     sdf = sc["sdf"]
 
     def query_func(points):
-        with torch.no_grad():
-            return sdf.forward(points.reshape(-1, 3), RATIO).reshape(1, 1, -1)
+        # discretizeSDF's closure (network.py:293-295) only needs the SDF value: the sdf-only last
+        # layer skips the 256-d feature the reference computes and throws away here
+        return sdf.forward_fused(points.reshape(-1, 3), RATIO, False, False)[0].reshape(1, 1, -1)
 
     eng = Seg3dLossless(query_func=query_func, b_min=[-1.0, -1.0, -1.0], b_max=[1.0, 1.0, 1.0],
                         resolutions=sc["synth"].MC_LADDER_257, align_corners=False, balance_value=0.0,

@@ -255,6 +255,34 @@ int sr_shade_geometry(const sr_mlp_desc* sdf, const sr_mlp_desc* dnet, const sr_
                       float* feat, int nfeat, float* dpos, uint8_t* inv_ok, cudaStream_t s);
 
 /* ------------------------------------------------------------------------------------------
+ * Tensor-core engine for the dense layers (tcgen05 + TMEM + TMA bulk copies): fp32-faithful
+ * BF16x3 split GEMM, one launch per layer,  C = act(A * W^T + b)  with the epilogue (bias,
+ * activation, forward-mode tangent scaling, skip concat, re-split) fused.  Operands are kept in
+ * global memory in the UMMA canonical tile layout (see csrc/tc_gemm.cu):
+ *   sr_tc_act_bytes(M,K) / sr_tc_weight_bytes(N,K): buffer sizes of tiled activations / weights
+ *   sr_tc_pack_rows    : fp32 row-major [M][K] (ld) -> tiled bf16x3 activations
+ *   sr_tc_pack_weights : fp32 row-major [N][K] (ld) effective weights -> tiled bf16x3
+ *   sr_tc_linear       : one layer. A (tiled, K), W (tiled, N x K), bias [pad256(N)];
+ *                        n_valid output columns; ch = rows per point (1, or 4 = value + 3
+ *                        tangents: tangent rows get act'(z_value) * acc, no bias);
+ *                        A_next (tiled, K_next columns, may be NULL) receives scale*act(.) with
+ *                        columns [n_valid, n_valid+skip_n) taken from skip_src (the skip concat of
+ *                        network.py:88-89) and the rest zero; out (fp32 [M][out_ld], may be NULL)
+ *                        receives columns [0,n_valid); dstash (fp32 [M][pad256(N)], may be NULL)
+ *                        receives act'(z) of value rows.
+ * Replaces the nn.Linear / cuBLAS calls of ImplicitNetwork / MLPTranslator / RenderNet for
+ * large batches (model/network.py:85-94, Deformer.py:64-69, RenderNet.py:80-88).
+ * ------------------------------------------------------------------------------------------ */
+int64_t sr_tc_act_bytes(int64_t M, int K);
+int64_t sr_tc_weight_bytes(int N, int K);
+int sr_tc_pack_rows(const float* src, int64_t M, int K, int ld, void* dst, cudaStream_t s);
+int sr_tc_pack_weights(const float* w, int N, int K, int ld, void* dst, cudaStream_t s);
+int sr_tc_linear(const void* A, const void* W, const float* bias, int64_t M, int N, int K,
+                 int n_valid, int act, int ch, void* A_next, int K_next, float scale,
+                 const float* skip_src, int skip_n, int skip_ld, float* out, int out_ld,
+                 float* dstash, cudaStream_t s);
+
+/* ------------------------------------------------------------------------------------------
  * Coarse-to-fine SDF grid plumbing (Seg3dLossless, MCAcc/seg3d_lossless.py:266-372).
  *   cand[z,y,x] = any(flag over the zero-padded 3x3x3 neighbourhood)
  *                 && !calculated[z*sz, y*sy, x*sx]

@@ -522,3 +522,49 @@ def seg3d_candidates(flag, calculated, stride_zyx):
                                       int(stride_zyx[0]), int(stride_zyx[1]), int(stride_zyx[2]),
                                       fD, fH, fW, _stream()), "seg3d_candidates")
     return cand
+
+
+# ------------------------------------------------------------------------------------------------
+# Tensor-core (tcgen05, BF16x3) layer engine
+# ------------------------------------------------------------------------------------------------
+def tc_pack_rows(x):
+    """fp32 [M,K] -> tiled bf16x3 activation buffer (uint8 tensor)."""
+    _need_cuda(x)
+    x = x.contiguous().float()
+    M, K = x.shape
+    lib = _lib.load()
+    buf = torch.empty((lib.sr_tc_act_bytes(M, K),), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.sr_tc_pack_rows(_p(x), M, K, K, _p(buf), _stream()), "tc_pack_rows")
+    return buf
+
+
+def tc_pack_weights(w):
+    """effective weights fp32 [N,K] -> tiled bf16x3 weight buffer (uint8 tensor)."""
+    _need_cuda(w)
+    w = w.contiguous().float()
+    N, K = w.shape
+    lib = _lib.load()
+    buf = torch.empty((lib.sr_tc_weight_bytes(N, K),), dtype=torch.uint8, device=w.device)
+    with torch.cuda.device(w.device):
+        check(lib.sr_tc_pack_weights(_p(w), N, K, K, _p(buf), _stream()), "tc_pack_weights")
+    return buf
+
+
+def tc_linear(A, W, bias, M, N, K, n_valid, act, ch=1, K_next=0, scale=1.0, skip_src=None, skip_n=0,
+              want_out=False, want_dstash=False):
+    """One layer on the tensor-core engine.  Returns (A_next | None, out | None, dstash | None)."""
+    lib = _lib.load()
+    dev = A.device
+    A_next = torch.empty((lib.sr_tc_act_bytes(M, K_next),), dtype=torch.uint8, device=dev) if K_next else None
+    out = torch.empty((M, n_valid), dtype=torch.float32, device=dev) if want_out else None
+    npad = (N + 255) // 256 * 256
+    ds = torch.empty((M, npad), dtype=torch.float32, device=dev) if want_dstash else None
+    b = torch.zeros((npad,), dtype=torch.float32, device=dev)
+    b[:bias.numel()] = bias.reshape(-1)
+    with torch.cuda.device(dev):
+        check(lib.sr_tc_linear(_p(A), _p(W), _p(b), M, N, K, n_valid, int(act), int(ch), _p(A_next),
+                               int(K_next), float(scale), _p(skip_src), int(skip_n),
+                               skip_src.shape[1] if skip_src is not None else 0, _p(out),
+                               n_valid if want_out else 0, _p(ds), _stream()), "tc_linear")
+    return A_next, out, ds

@@ -492,3 +492,43 @@ def test_seg3d_lossless_vs_golden_and_mc(cuda_dev):
         assert v.shape[0] > 100
         if name == "seg3d.npz":  # closed surface inside the box (the anisotropic box clips it)
             assert (f >= 0).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# Tensor-core engine (tcgen05, BF16x3 split) -- fp32-faithful GEMM layers
+# ------------------------------------------------------------------------------------------------
+def test_tc_linear_bf16x3_matches_fp64(cuda_dev):
+    from selfreconcode_b200 import ops
+    from selfreconcode_b200._lib import SR_ACT_NONE, SR_ACT_SOFTPLUS100, SR_ACT_RELU
+    g = torch.Generator().manual_seed(7)
+    for M, K, N in ((300, 64, 512), (1000, 512, 512), (129, 192, 473)):
+        x = torch.randn(M, K, generator=g).to(cuda_dev)
+        w = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda_dev)
+        b = (0.1 * torch.randn(N, generator=g)).to(cuda_dev)
+        A = ops.tc_pack_rows(x)
+        W = ops.tc_pack_weights(w)
+        ref = (x.double() @ w.double().t() + b.double())
+        _, out, _ = ops.tc_linear(A, W, b, M, N, K, N, SR_ACT_NONE, want_out=True)
+        err = rel_err(out.cpu().numpy(), ref.cpu().numpy())
+        f32 = rel_err((x @ w.t() + b).cpu().numpy(), ref.cpu().numpy())
+        assert err < 2e-6, (M, K, N, err, f32)   # fp32-class accuracy from six bf16 products
+        # chained: hidden layer (softplus) written in the tiled layout, consumed by a second layer
+        w2 = (torch.randn(3, N, generator=g) / N ** 0.5).to(cuda_dev)
+        b2 = torch.zeros(3, device=cuda_dev)
+        A1, _, _ = ops.tc_linear(A, W, b, M, N, K, N, SR_ACT_SOFTPLUS100, K_next=(N + 31) // 32 * 32)
+        _, out2, _ = ops.tc_linear(A1, ops.tc_pack_weights(w2), b2, M, 3, (N + 31) // 32 * 32, 3, SR_ACT_NONE,
+                                   want_out=True)
+        h = torch.nn.functional.softplus(ref, beta=100)
+        ref2 = h @ w2.double().t()
+        assert rel_err(out2.cpu().numpy(), ref2.cpu().numpy()) < 1e-5
+    # forward-mode tangent rows (4 rows per point: value, d/dx, d/dy, d/dz)
+    P, K, N = 64, 64, 256
+    x = torch.randn(P * 4, K, generator=g).to(cuda_dev)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda_dev)
+    b = (0.05 * torch.randn(N, generator=g)).to(cuda_dev)
+    _, out, _ = ops.tc_linear(ops.tc_pack_rows(x), ops.tc_pack_weights(w), b, P * 4, N, K, N, SR_ACT_RELU, ch=4,
+                              want_out=True)
+    z = (x.double() @ w.double().t()).view(P, 4, N)
+    zv = z[:, 0] + b.double()
+    exp = torch.cat([torch.relu(zv)[:, None], (zv > 0).double()[:, None] * z[:, 1:]], 1).view(P * 4, N)
+    assert rel_err(out.cpu().numpy(), exp.cpu().numpy()) < 1e-5
