@@ -273,6 +273,11 @@ int sr_shade_geometry(const sr_mlp_desc* sdf, const sr_mlp_desc* dnet, const sr_
  * Replaces the nn.Linear / cuBLAS calls of ImplicitNetwork / MLPTranslator / RenderNet for
  * large batches (model/network.py:85-94, Deformer.py:64-69, RenderNet.py:80-88).
  * ------------------------------------------------------------------------------------------ */
+/* embedded network input, fp32 [P*ch][ld]: PE(p) (+ cond[b]); tangent rows hold d/dp of it.
+ * pe_w is a HOST array of `multires` band weights. */
+int sr_tc_embed(const float* pts, int64_t P, int multires, const float* pe_w, int ch,
+                const float* conds, const int64_t* batch_inds, int64_t pts_per_frame, int condlen,
+                float* out, int ld, cudaStream_t s);
 int64_t sr_tc_act_bytes(int64_t M, int K);
 int64_t sr_tc_weight_bytes(int N, int K);
 int sr_tc_pack_rows(const float* src, int64_t M, int K, int ld, void* dst, cudaStream_t s);

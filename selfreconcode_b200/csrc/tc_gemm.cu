@@ -24,7 +24,8 @@
 namespace sr_tc {
 
 constexpr int BM = 128, BN = 256, BK = 32, STAGES = 3;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;               // two per TMEM lane quarter, each takes half the columns
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int A_PLANE = BM * BK;          // elements
 constexpr int W_PLANE = BN * BK;
 constexpr int A_STAGE = 3 * A_PLANE;      // 12288 bf16 = 24 KB
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { sr_mbar_init(&full[i], 1); sr_mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { sr_mbar_init(&tfull[i], 1); sr_mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { sr_mbar_init(&tfull[i], 1); sr_mbar_init(&tempty[i], kEpiWarps); }
     sr_fence_barrier_init();
   }
   if (warp == 1) {  // TMEM: all 512 columns (two 256-column accumulators)
@@ -214,61 +215,82 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(const __grid_cons
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;       // which half of the 256 accumulator columns
     const int row_in_tile = q * 32 + lane;
+    const bool is_val = (a.ch == 1) || ((lane & 3) == 0);
+    const size_t ds_ld = (size_t)a.NT * BN;
     int buf = 0;
     uint32_t bphase = 0;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const long long mt = t / a.NT;
       const int nt = (int)(t % a.NT);
       const long long row = mt * BM + row_in_tile;
+      const bool row_ok = row < a.M;
       sr_mbar_wait(&tfull[buf], bphase);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * BN;
-      const bool is_val = (a.ch == 1) || ((lane & 3) == 0);
-      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+      for (int chunk = half * 4; chunk < half * 4 + 4; ++chunk) {
         uint32_t v[32];
         tmem_ld32(taddr0 + chunk * 32, v);
         const int c0 = nt * BN + chunk * 32;
         float o[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int c = c0 + j;
-          const float acc = __uint_as_float(v[j]);
-          float d = 1.f, val;
-          const float z = acc + (is_val ? __ldg(a.bias + c) : 0.f);
-          if (is_val) val = act_fn(a.act, z, d);
-          else val = 0.f;
-          if (a.ch == 4) {
-            const float dv = __shfl_sync(0xffffffffu, d, lane & ~3);  // act'(z) of the value row
-            if (!is_val) val = dv * acc;
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + c0) + j4);
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = j4 * 4 + jj;
+            const float acc = __uint_as_float(v[j]);
+            float d = 1.f, val = 0.f;
+            if (is_val) val = act_fn(a.act, acc + bb[jj], d);
+            if (a.ch == 4) {
+              const float dv = __shfl_sync(0xffffffffu, d, lane & ~3);  // act'(z) of the value row
+              if (!is_val) val = dv * acc;
+            }
+            o[j] = val * a.scale;
+            v[j] = __float_as_uint(d);
           }
-          if (a.dstash != nullptr && is_val && row < a.M) a.dstash[(size_t)row * ((size_t)a.NT * BN) + c] = d;
-          val *= a.scale;
-          if (c >= a.n) {
-            val = 0.f;
-            if (a.skip_src != nullptr && c < a.n + a.skip_n && row < a.M)
-              val = a.skip_src[(size_t)row * a.skip_ld + (c - a.n)] * a.scale;
+        }
+        if (a.dstash != nullptr && is_val && row_ok) {
+          float4* dd = reinterpret_cast<float4*>(a.dstash + (size_t)row * ds_ld + c0);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4)
+            dd[j4] = make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]),
+                                 __uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3]));
+        }
+        if (c0 + 32 > a.n) {  // tail chunk: zero padding / skip-connection columns (uniform branch)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int c = c0 + j;
+            if (c >= a.n) {
+              float val = 0.f;
+              if (a.skip_src != nullptr && c < a.n + a.skip_n && row_ok)
+                val = a.skip_src[(size_t)row * a.skip_ld + (c - a.n)] * a.scale;
+              o[j] = val;
+            }
           }
-          o[j] = val;
         }
         if (a.A_next != nullptr) {
           const int kcn = c0 >> 5;  // next layer's k chunk
           if (kcn < a.KCn) {
+            __nv_bfloat16* base = a.A_next + a_tile_off(mt, kcn, a.KCn, 0) +
+                                  (size_t)(row_in_tile >> 3) * 64 + (row_in_tile & 7) * 8;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               __align__(16) __nv_bfloat16 p1[8], p2[8], p3[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) split3(o[g * 8 + e], p1[e], p2[e], p3[e]);
-              const size_t off = (size_t)g * (BM * 8) + (size_t)(row_in_tile >> 3) * 64 + (row_in_tile & 7) * 8;
-              *reinterpret_cast<uint4*>(a.A_next + a_tile_off(mt, kcn, a.KCn, 0) + off) = *reinterpret_cast<uint4*>(p1);
-              *reinterpret_cast<uint4*>(a.A_next + a_tile_off(mt, kcn, a.KCn, 1) + off) = *reinterpret_cast<uint4*>(p2);
-              *reinterpret_cast<uint4*>(a.A_next + a_tile_off(mt, kcn, a.KCn, 2) + off) = *reinterpret_cast<uint4*>(p3);
+              __nv_bfloat16* dst = base + (size_t)g * (BM * 8);
+              *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(p1);
+              *reinterpret_cast<uint4*>(dst + A_PLANE) = *reinterpret_cast<uint4*>(p2);
+              *reinterpret_cast<uint4*>(dst + 2 * A_PLANE) = *reinterpret_cast<uint4*>(p3);
             }
           }
         }
-        if (a.out != nullptr && row < a.M) {
+        if (a.out != nullptr && row_ok && c0 < a.n) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (c0 + j < a.n) a.out[(size_t)row * a.out_ld + c0 + j] = o[j];
@@ -341,9 +363,72 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int N, int K, i
   }
 }
 
+// Embedded network input, fp32 row-major [P*ch][ld]: PE(p) (+ cond[b]) for value rows and
+// d/dp_t of it for tangent rows (model/Embedder.py:11-32).  One thread per element (coalesced).
+struct EmbedArgs {
+  const float* pts;
+  long long P;
+  int multires;
+  float pe_w[16];
+  int ch;
+  const float* conds;
+  const long long* batch_inds;
+  long long pts_per_frame;
+  int condlen;
+  float* out;
+  int ld;
+};
+__global__ void embed_kernel(const __grid_constant__ EmbedArgs a) {
+  const long long total = a.P * a.ch * (long long)a.ld;
+  const int pe_dim = 3 + 6 * a.multires;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % a.ld);
+    const long long row = idx / a.ld;
+    const long long p = row / a.ch;
+    const int t = (int)(row % a.ch);  // 0 = value, 1..3 = d/dp_{t-1}
+    float v = 0.f;
+    if (k < 3) {
+      v = t == 0 ? a.pts[p * 3 + k] : (t - 1 == k ? 1.f : 0.f);
+    } else if (k < pe_dim) {
+      const int b = (k - 3) / 6, w6 = (k - 3) % 6, j = w6 % 3;
+      const bool is_cos = w6 >= 3;
+      if (t == 0 || t - 1 == j) {
+        const float freq = (float)(1 << b);
+        float sn, cs;
+        sincosf(a.pts[p * 3 + j] * freq, &sn, &cs);
+        const float w = a.pe_w[b];
+        if (t == 0) v = w * (is_cos ? cs : sn);
+        else v = is_cos ? -(w * freq) * sn : (w * freq) * cs;
+      }
+    } else if (k < pe_dim + a.condlen) {
+      if (t == 0) {
+        const long long bi = a.batch_inds ? a.batch_inds[p] : (a.pts_per_frame > 0 ? p / a.pts_per_frame : 0);
+        v = a.conds[bi * a.condlen + (k - pe_dim)];
+      }
+    }
+    a.out[idx] = v;
+  }
+}
+
 }  // namespace sr_tc
 
 extern "C" {
+
+int sr_tc_embed(const float* pts, int64_t P, int multires, const float* pe_w, int ch,
+                const float* conds, const int64_t* batch_inds, int64_t pts_per_frame, int condlen,
+                float* out, int ld, cudaStream_t s) {
+  if (!pts || !out || !pe_w || P <= 0 || (ch != 1 && ch != 4) || multires < 0 || multires > 16) return SR_EINVAL;
+  if (ld < 3 + 6 * multires + condlen || (condlen > 0 && !conds)) return SR_EINVAL;
+  sr_tc::EmbedArgs a;
+  a.pts = pts; a.P = P; a.multires = multires; a.ch = ch; a.conds = conds;
+  a.batch_inds = (const long long*)batch_inds; a.pts_per_frame = pts_per_frame; a.condlen = condlen;
+  a.out = out; a.ld = ld;
+  for (int i = 0; i < 16; ++i) a.pe_w[i] = i < multires ? pe_w[i] : 0.f;
+  const long long total = P * ch * (long long)ld;
+  sr_tc::embed_kernel<<<sr_grid_for(total, 256, 8), 256, 0, s>>>(a);
+  return sr_launch_status();
+}
 
 int64_t sr_tc_act_bytes(int64_t M, int K) {
   const int64_t MT = (M + sr_tc::BM - 1) / sr_tc::BM, KC = (K + 31) / 32;

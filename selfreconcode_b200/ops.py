@@ -15,6 +15,13 @@ from ._lib import MlpDesc, LbsParams, TraceParams
 from ._lib import check as _check
 
 
+import os as _os
+
+# Tensor-core engine switch: large batches go to the tcgen05 BF16x3 layer GEMMs, small ones to the
+# fused fp32 FFMA engine (one persistent kernel, lower latency).  SELFRECON_B200_TC=0 disables it.
+TC_ENABLED = _os.environ.get("SELFRECON_B200_TC", "1") != "0"
+TC_MIN_POINTS = int(_os.environ.get("SELFRECON_B200_TC_MIN_POINTS", "16384"))
+
 LAUNCHES = 0  # kernels launched by this module since it was last reset (bench.py reads it)
 
 _KERNELS_PER_CALL = {"mc_count": 2}
@@ -568,3 +575,83 @@ def tc_linear(A, W, bias, M, N, K, n_valid, act, ch=1, K_next=0, scale=1.0, skip
                                skip_src.shape[1] if skip_src is not None else 0, _p(out),
                                n_valid if want_out else 0, _p(ds), _stream()), "tc_linear")
     return A_next, out, ds
+
+
+class TcNet:
+    """Tensor-core view of a FusedMLP: the same folded weights packed as tiled bf16x3 operands.
+    Built lazily from the FusedMLP's un-transposed padded copies (`wb`), cached on the FusedMLP."""
+
+    def __init__(self, fused):
+        self.fused = fused
+        d = fused.desc
+        self.layers = []
+        lib = _lib.load()
+        dev = fused.device
+        wbs = [b for b in fused.bufs]
+        for i in range(d.n_layers):
+            ly = d.layer[i]
+            n, k = ly.n, ly.k
+            wb = [b for b in wbs if b is not None and b.data_ptr() == ly.wb][0]
+            bias = [b for b in wbs if b is not None and b.data_ptr() == ly.bias][0]
+            W = torch.empty((lib.sr_tc_weight_bytes(n, k),), dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                check(lib.sr_tc_pack_weights(_p(wb), n, k, wb.shape[1], _p(W), _stream()), "tc_pack_weights")
+            npad = _pad(n, 256)
+            b = torch.zeros((npad,), dtype=torch.float32, device=dev)
+            b[:n] = bias[:n]
+            self.layers.append(dict(W=W, bias=b, n=n, k=k, act=ly.act, skip=bool(ly.skip)))
+
+
+def tc_net(fused):
+    t = getattr(fused, "_tc", None)
+    if t is None:
+        t = TcNet(fused)
+        fused._tc = t
+    return t
+
+
+def tc_mlp_forward(fused, pts, ch=1, conds=None, batch_inds=None, pts_per_frame=0, n_out=None,
+                   want_dstash=False):
+    """Whole MLP on the tensor-core engine: embed -> pack -> one tcgen05 launch per layer.
+    Returns out fp32 [P*ch, n_out] (last-layer outputs; tangent rows hold d out / d p_t)."""
+    _need_cuda(pts)
+    net = tc_net(fused)
+    d = fused.desc
+    dev = pts.device
+    pts = pts.contiguous().float().view(-1, 3)
+    P = pts.shape[0]
+    M = P * ch
+    condlen = conds.shape[-1] if conds is not None else 0
+    ld = _pad(d.d_in, 32)
+    lib = _lib.load()
+    emb = torch.empty((M, ld), dtype=torch.float32, device=dev)
+    pw = (C.c_float * 16)(*[d.pe_w[i] for i in range(16)])
+    bi = batch_inds.contiguous().to(torch.int64) if batch_inds is not None else None
+    cd = conds.detach().contiguous().float() if conds is not None else None
+    with torch.cuda.device(dev):
+        check(lib.sr_tc_embed(_p(pts), P, d.multires, pw, ch, _p(cd), _p(bi), int(pts_per_frame), condlen,
+                              _p(emb), ld, _stream()), "tc_embed")
+        A = torch.empty((lib.sr_tc_act_bytes(M, ld),), dtype=torch.uint8, device=dev)
+        check(lib.sr_tc_pack_rows(_p(emb), M, ld, ld, _p(A), _stream()), "tc_pack_rows")
+        K = ld
+        out = None
+        stashes = []
+        L = len(net.layers)
+        for i, ly in enumerate(net.layers):
+            last = i == L - 1
+            nxt = net.layers[i + 1] if not last else None
+            nv = ly["n"] if not (last and n_out) else n_out
+            Kn = _pad(nxt["k"], 32) if nxt else 0
+            skip_next = bool(nxt and nxt["skip"])
+            A_next = torch.empty((lib.sr_tc_act_bytes(M, Kn),), dtype=torch.uint8, device=dev) if nxt else None
+            o = torch.empty((M, nv), dtype=torch.float32, device=dev) if last else None
+            ds = torch.empty((M, _pad(ly["n"], 256)), dtype=torch.float32, device=dev) \
+                if (want_dstash and not last) else None
+            check(lib.sr_tc_linear(_p(A), _p(ly["W"]), _p(ly["bias"]), M, ly["n"], K, nv, ly["act"], ch,
+                                   _p(A_next), Kn, 0.7071067811865476 if skip_next else 1.0,
+                                   _p(emb) if skip_next else None, d.d_in if skip_next else 0, ld, _p(o),
+                                   nv if last else 0, _p(ds), _stream()), "tc_linear")
+            if ds is not None:
+                stashes.append(ds)
+            A, K, out = A_next, Kn, o
+    return (out, stashes) if want_dstash else out
