@@ -316,6 +316,7 @@ def main():
         _, _, counters = ops.trace_surface_points(sdf_only, dnet, lbs, sc["cam"]["cam_pos"], rays_d, init_d, bi_d,
                                                   sc["conds"][0], 5e-5, sc["ang"], 3.05, 1.0, 10,
                                                   return_counters=True)
+        trace_mode = "tc" if (ops.TC_ENABLED and n_rays >= ops.TC_MIN_POINTS) else "reverse"
         b.record()
         torch.cuda.synchronize()
         tk.append(a.elapsed_time(b))
@@ -385,13 +386,18 @@ def main():
         "e2e": {"value": total_rays / (e2e_t * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms": e2e_t},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "trace_kernel (11 launches per trace)", "bound": "tensor",
-                     "achieved": trace_flops / trace_s / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s",
-                     "frac": trace_flops / trace_s / 1e12 / pk["tensor"], "traffic": None,
+        "roofline": {"kernel": ("tc_layer_kernel (tcgen05 BF16x3 GEMM layers of the tracer: 28 fwd+bwd layer "
+                                "launches per iteration)" if trace_mode == "tc" else
+                                "trace_rev_kernel (fused fp32 FFMA, 11 launches per trace)"),
+                     "bound": "tensor", "achieved": trace_flops / trace_s / 1e12, "peak": pk["tensor"],
+                     "unit": "TFLOP/s", "frac": trace_flops / trace_s / 1e12 / pk["tensor"], "traffic": None,
                      "peak_source": pk["src"] + " bf16 cuBLAS burst",
-                     "note": "fp32 FFMA engine (no tensor cores yet): fp32 FFMA peak is ~72 TFLOP/s; "
-                             "algorithmic FLOPs = (rays + 3*ray_iterations) * 5.680 MFLOP",
-                     "ms": trace_s * 1e3, "ray_iterations": int(ray_iters)},
+                     "note": "algorithmic FLOPs = (rays + 3*ray_iterations) * 5.680 MFLOP (SURVEY 8d) over the whole "
+                             "trace (all launches, incl. embed / LBS / update kernels); fp32-faithful BF16x3 "
+                             "costs 6 bf16 MMAs per product, so the ceiling of this path is peak/6 = %.0f TFLOP/s"
+                             % (pk["tensor"] / 6.0),
+                     "frac_of_bf16x3_ceiling": trace_flops / trace_s / 1e12 / (pk["tensor"] / 6.0),
+                     "ms": trace_s * 1e3, "ray_iterations": int(ray_iters), "engine": trace_mode},
         "roofline_mc": {"kernel": "mc_classify+mc_scan+mc_emit", "bound": "hbm",
                         "achieved": mc_bytes / mc_s / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                         "frac": mc_bytes / mc_s / 1e9 / pk["hbm"], "traffic": None, "ms": mc_s * 1e3,

@@ -268,8 +268,11 @@ int sr_shade_geometry(const sr_mlp_desc* sdf, const sr_mlp_desc* dnet, const sr_
  *                        A_next (tiled, K_next columns, may be NULL) receives scale*act(.) with
  *                        columns [n_valid, n_valid+skip_n) taken from skip_src (the skip concat of
  *                        network.py:88-89) and the rest zero; out (fp32 [M][out_ld], may be NULL)
- *                        receives columns [0,n_valid); dstash (fp32 [M][pad256(N)], may be NULL)
- *                        receives act'(z) of value rows.
+ *                        receives result columns [out_col0, out_col0+out_n); dstash (fp32
+ *                        [M][pad256(N)], may be NULL) receives act'(z) of value rows; mul_src
+ *                        (fp32 [M][mul_ld], may be NULL) switches the epilogue to
+ *                        out = acc * mul_src (the reverse-mode sweep: delta * act'); m_dev
+ *                        (may be NULL) is a device-side row count <= M (active rays).
  * Replaces the nn.Linear / cuBLAS calls of ImplicitNetwork / MLPTranslator / RenderNet for
  * large batches (model/network.py:85-94, Deformer.py:64-69, RenderNet.py:80-88).
  * ------------------------------------------------------------------------------------------ */
@@ -277,15 +280,31 @@ int sr_shade_geometry(const sr_mlp_desc* sdf, const sr_mlp_desc* dnet, const sr_
  * pe_w is a HOST array of `multires` band weights. */
 int sr_tc_embed(const float* pts, int64_t P, int multires, const float* pe_w, int ch,
                 const float* conds, const int64_t* batch_inds, int64_t pts_per_frame, int condlen,
-                float* out, int ld, cudaStream_t s);
+                float* out, int ld, const int32_t* index /* optional active list */,
+                const int32_t* m_dev /* optional device-side count */, cudaStream_t s);
 int64_t sr_tc_act_bytes(int64_t M, int K);
 int64_t sr_tc_weight_bytes(int N, int K);
-int sr_tc_pack_rows(const float* src, int64_t M, int K, int ld, void* dst, cudaStream_t s);
+int sr_tc_pack_rows(const float* src, int64_t M, int K, int ld, void* dst, const int32_t* m_dev,
+                    cudaStream_t s);
 int sr_tc_pack_weights(const float* w, int N, int K, int ld, void* dst, cudaStream_t s);
 int sr_tc_linear(const void* A, const void* W, const float* bias, int64_t M, int N, int K,
                  int n_valid, int act, int ch, void* A_next, int K_next, float scale,
                  const float* skip_src, int skip_n, int skip_ld, float* out, int out_ld,
-                 float* dstash, cudaStream_t s);
+                 int out_col0, int out_n, float* dstash, const float* mul_src, int mul_ld,
+                 const int32_t* m_dev, cudaStream_t s);
+
+/* Pointwise stages of the tensor-core tracer (one OptimizeSurfacePs iteration =
+ * embed -> sr_tc_linear x layers (forward, act' stashed) -> sr_tc_trace_mid -> sr_tc_linear x
+ * layers (reverse sweep, mul_src = stash) -> sr_tc_trace_update).  All take an optional active
+ * list + device-side count so the host never synchronises.  pw_s / pw_d are HOST arrays. */
+int sr_tc_trace_mid(const int32_t* index, const int32_t* m_dev, int64_t P, const float* pts,
+                    const float* rays, const int64_t* batch_inds, const float* f, const float* off,
+                    const sr_lbs_params* lbs, const sr_trace_params* tp, int do_update,
+                    uint8_t* converged, float* dsdf, float* ddef, int ld, float* aux, cudaStream_t s);
+int sr_tc_trace_update(const int32_t* index, const int32_t* m_dev, int64_t P, float* pts,
+                       const float* gs, int gs_ld, const float* gskip, int gk_ld, const float* gd,
+                       int gd_ld, const float* aux, int mr_s, const float* pw_s, int mr_d,
+                       const float* pw_d, int32_t* active_out, int32_t* counter_out, cudaStream_t s);
 
 /* ------------------------------------------------------------------------------------------
  * Coarse-to-fine SDF grid plumbing (Seg3dLossless, MCAcc/seg3d_lossless.py:266-372).

@@ -91,13 +91,18 @@ SIGNATURES = {
     "sr_shade_geometry": (C.c_int, [C.POINTER(MlpDesc), C.POINTER(MlpDesc), C.POINTER(LbsParams),
                                     c_f, c_f, c_f, c_f, i32, i64, c_f, c_f, c_f, i32, c_f, c_f,
                                     stream_t]),
-    "sr_tc_embed": (C.c_int, [c_f, i64, i32, C.POINTER(f32), i32, c_f, c_f, i64, i32, c_f, i32, stream_t]),
+    "sr_tc_embed": (C.c_int, [c_f, i64, i32, C.POINTER(f32), i32, c_f, c_f, i64, i32, c_f, i32, c_f, c_f,
+                              stream_t]),
     "sr_tc_act_bytes": (i64, [i64, i32]),
     "sr_tc_weight_bytes": (i64, [i32, i32]),
-    "sr_tc_pack_rows": (C.c_int, [c_f, i64, i32, i32, c_f, stream_t]),
+    "sr_tc_pack_rows": (C.c_int, [c_f, i64, i32, i32, c_f, c_f, stream_t]),
     "sr_tc_pack_weights": (C.c_int, [c_f, i32, i32, i32, c_f, stream_t]),
     "sr_tc_linear": (C.c_int, [c_f, c_f, c_f, i64, i32, i32, i32, i32, i32, c_f, i32, f32, c_f, i32,
-                               i32, c_f, i32, c_f, stream_t]),
+                               i32, c_f, i32, i32, i32, c_f, c_f, i32, c_f, stream_t]),
+    "sr_tc_trace_mid": (C.c_int, [c_f, c_f, i64, c_f, c_f, c_f, c_f, c_f, C.POINTER(LbsParams),
+                                  C.POINTER(TraceParams), i32, c_f, c_f, c_f, i32, c_f, stream_t]),
+    "sr_tc_trace_update": (C.c_int, [c_f, c_f, i64, c_f, c_f, i32, c_f, i32, c_f, i32, c_f, i32,
+                                     C.POINTER(f32), i32, C.POINTER(f32), c_f, c_f, stream_t]),
     "sr_seg3d_candidates": (C.c_int, [c_f, c_f, c_f, i32, i32, i32, i32, i32, i32, i32, i32, i32,
                                       stream_t]),
 }

@@ -113,6 +113,11 @@ struct LayerArgs {
   float* out;               // fp32 row-major [M][out_ld] (last layer), columns [0, n)
   int out_ld;
   float* dstash;            // fp32 row-major [M][NT*256] act'(z) of value rows (reverse mode) or null
+  const float* mul_src;     // fp32 [M][mul_ld] or null: out = acc * mul_src (backward sweep: act' stash)
+  int mul_ld;
+  int out_col0;             // `out` receives columns [out_col0, out_col0 + out_n) of the result
+  int out_n;
+  const int* m_dev;         // optional device-side row count (active rays); M is the upper bound
 };
 
 __device__ __forceinline__ float act_fn(int act, float z, float& d) {
@@ -157,7 +162,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const long long ntiles = (long long)a.MT * a.NT;
+  long long Mrows = a.M;
+  int MTe = a.MT;
+  if (a.m_dev != nullptr) {
+    const long long md = (long long)(*a.m_dev);
+    Mrows = md < a.M ? md : a.M;
+    MTe = (int)((Mrows + BM - 1) / BM);
+  }
+  const long long ntiles = (long long)MTe * a.NT;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -227,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(const __grid_cons
       const long long mt = t / a.NT;
       const int nt = (int)(t % a.NT);
       const long long row = mt * BM + row_in_tile;
-      const bool row_ok = row < a.M;
+      const bool row_ok = row < Mrows;
       sr_mbar_wait(&tfull[buf], bphase);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * BN;
@@ -245,7 +257,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(const __grid_cons
             const int j = j4 * 4 + jj;
             const float acc = __uint_as_float(v[j]);
             float d = 1.f, val = 0.f;
-            if (is_val) val = act_fn(a.act, acc + bb[jj], d);
+            if (a.mul_src != nullptr) {
+              // reverse sweep: delta * act'(z) for the columns that continue; columns >= n (the
+              // skip-connection part of a skip layer's input gradient) pass through unscaled by act'
+              val = acc;
+              if (c0 + j < a.n) val = row_ok ? acc * __ldg(a.mul_src + (size_t)row * a.mul_ld + c0 + j) : 0.f;
+            } else if (is_val) val = act_fn(a.act, acc + bb[jj], d);
             if (a.ch == 4) {
               const float dv = __shfl_sync(0xffffffffu, d, lane & ~3);  // act'(z) of the value row
               if (!is_val) val = dv * acc;
@@ -260,6 +277,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(const __grid_cons
           for (int j4 = 0; j4 < 8; ++j4)
             dd[j4] = make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]),
                                  __uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3]));
+        }
+        if (a.out != nullptr && row_ok && c0 < a.out_col0 + a.out_n && c0 + 32 > a.out_col0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int c = c0 + j - a.out_col0;
+            if (c >= 0 && c < a.out_n) a.out[(size_t)row * a.out_ld + c] = o[j];
+          }
         }
         if (c0 + 32 > a.n) {  // tail chunk: zero padding / skip-connection columns (uniform branch)
 #pragma unroll
@@ -290,11 +314,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(const __grid_cons
             }
           }
         }
-        if (a.out != nullptr && row_ok && c0 < a.n) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c0 + j < a.n) a.out[(size_t)row * a.out_ld + c0 + j] = o[j];
-        }
       }
       tc_fence_before();
       __syncwarp();
@@ -313,7 +332,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(const __grid_cons
 // ---- packing kernels -------------------------------------------------------------------------
 // fp32 row-major [M][K] (ld) -> tiled bf16x3 activations with KC = ceil(Kpad/32) chunks
 __global__ void pack_rows_kernel(const float* __restrict__ src, long long M, int K, int ld,
-                                 __nv_bfloat16* __restrict__ dst, int KC, long long MT) {
+                                 __nv_bfloat16* __restrict__ dst, int KC, long long MT,
+                                 const int* __restrict__ m_dev) {
+  if (m_dev != nullptr) {
+    const long long md = *m_dev;
+    M = md < M ? md : M;
+    MT = (M + BM - 1) / BM;
+  }
   const long long total = MT * BM * (long long)KC * 4;  // one thread per (row, k8 group)
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -377,15 +402,20 @@ struct EmbedArgs {
   int condlen;
   float* out;
   int ld;
+  const int* index;   // optional active list: row i embeds point index[i]
+  const int* m_dev;   // optional device-side count of active points
 };
 __global__ void embed_kernel(const __grid_constant__ EmbedArgs a) {
-  const long long total = a.P * a.ch * (long long)a.ld;
+  long long np = a.P;
+  if (a.m_dev != nullptr) { const long long md = *a.m_dev; np = md < np ? md : np; }
+  const long long total = np * a.ch * (long long)a.ld;
   const int pe_dim = 3 + 6 * a.multires;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(idx % a.ld);
     const long long row = idx / a.ld;
-    const long long p = row / a.ch;
+    const long long pi = row / a.ch;
+    const long long p = a.index ? (long long)a.index[pi] : pi;
     const int t = (int)(row % a.ch);  // 0 = value, 1..3 = d/dp_{t-1}
     float v = 0.f;
     if (k < 3) {
@@ -417,13 +447,13 @@ extern "C" {
 
 int sr_tc_embed(const float* pts, int64_t P, int multires, const float* pe_w, int ch,
                 const float* conds, const int64_t* batch_inds, int64_t pts_per_frame, int condlen,
-                float* out, int ld, cudaStream_t s) {
+                float* out, int ld, const int32_t* index, const int32_t* m_dev, cudaStream_t s) {
   if (!pts || !out || !pe_w || P <= 0 || (ch != 1 && ch != 4) || multires < 0 || multires > 16) return SR_EINVAL;
   if (ld < 3 + 6 * multires + condlen || (condlen > 0 && !conds)) return SR_EINVAL;
   sr_tc::EmbedArgs a;
   a.pts = pts; a.P = P; a.multires = multires; a.ch = ch; a.conds = conds;
   a.batch_inds = (const long long*)batch_inds; a.pts_per_frame = pts_per_frame; a.condlen = condlen;
-  a.out = out; a.ld = ld;
+  a.out = out; a.ld = ld; a.index = index; a.m_dev = m_dev;
   for (int i = 0; i < 16; ++i) a.pe_w[i] = i < multires ? pe_w[i] : 0.f;
   const long long total = P * ch * (long long)ld;
   sr_tc::embed_kernel<<<sr_grid_for(total, 256, 8), 256, 0, s>>>(a);
@@ -439,12 +469,13 @@ int64_t sr_tc_weight_bytes(int N, int K) {
   return NT * KC * 3 * sr_tc::W_PLANE * 2;
 }
 
-int sr_tc_pack_rows(const float* src, int64_t M, int K, int ld, void* dst, cudaStream_t s) {
+int sr_tc_pack_rows(const float* src, int64_t M, int K, int ld, void* dst, const int32_t* m_dev,
+                    cudaStream_t s) {
   if (!src || !dst || M <= 0 || K <= 0 || ld < K) return SR_EINVAL;
   const long long MT = (M + sr_tc::BM - 1) / sr_tc::BM;
   const int KC = (K + 31) / 32;
   const long long total = MT * sr_tc::BM * KC * 4;
-  sr_tc::pack_rows_kernel<<<sr_grid_for(total, 256, 8), 256, 0, s>>>(src, M, K, ld, (__nv_bfloat16*)dst, KC, MT);
+  sr_tc::pack_rows_kernel<<<sr_grid_for(total, 256, 8), 256, 0, s>>>(src, M, K, ld, (__nv_bfloat16*)dst, KC, MT, m_dev);
   return sr_launch_status();
 }
 
@@ -458,7 +489,9 @@ int sr_tc_pack_weights(const float* w, int N, int K, int ld, void* dst, cudaStre
 
 int sr_tc_linear(const void* A, const void* W, const float* bias, int64_t M, int N, int K, int n_valid,
                  int act, int ch, void* A_next, int K_next, float scale, const float* skip_src,
-                 int skip_n, int skip_ld, float* out, int out_ld, float* dstash, cudaStream_t s) {
+                 int skip_n, int skip_ld, float* out, int out_ld, int out_col0, int out_n,
+                 float* dstash, const float* mul_src, int mul_ld, const int32_t* m_dev,
+                 cudaStream_t s) {
   using namespace sr_tc;
   if (!A || !W || !bias || M <= 0 || N <= 0 || K <= 0 || (ch != 1 && ch != 4)) return SR_EINVAL;
   if (!A_next && !out) return SR_EINVAL;
@@ -468,7 +501,8 @@ int sr_tc_linear(const void* A, const void* W, const float* bias, int64_t M, int
   a.n = n_valid; a.act = act; a.ch = ch;
   a.A_next = (__nv_bfloat16*)A_next; a.KCn = A_next ? (K_next + 31) / 32 : 0;
   a.scale = scale; a.skip_src = skip_src; a.skip_n = skip_n; a.skip_ld = skip_ld;
-  a.out = out; a.out_ld = out_ld; a.dstash = dstash;
+  a.out = out; a.out_ld = out_ld; a.dstash = dstash; a.out_col0 = out_col0; a.out_n = out_n;
+  a.mul_src = mul_src; a.mul_ld = mul_ld; a.m_dev = m_dev;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);

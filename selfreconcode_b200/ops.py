@@ -446,9 +446,16 @@ def _trace_scratch(dev):
 
 def trace_surface_points(sdf_net, def_net, lbs, cam_pos, rays, init_pts, batch_inds, conds,
                          dthreshold=5e-5, athreshold=0.02, w1=3.05, w2=1.0, times=5,
-                         return_counters=False, mode="reverse"):
+                         return_counters=False, mode="auto"):
     """OptimizeSurfacePs (utils/FindSurfacePs.py:114-163): returns (points, converged).
-    times+1 launches are enqueued back to back; nothing syncs the host."""
+    Nothing syncs the host.  mode: "tc" = dense layers on the tensor-core engine (tcgen05 BF16x3,
+    reverse-mode sweeps), "reverse" / "forward" = fused fp32 FFMA engine (times+1 launches of one
+    persistent kernel), "auto" = "tc" for large ray sets, "reverse" otherwise."""
+    if mode == "auto":
+        mode = "tc" if (TC_ENABLED and init_pts.shape[0] >= TC_MIN_POINTS) else "reverse"
+    if mode == "tc":
+        return trace_surface_points_tc(sdf_net, def_net, lbs, cam_pos, rays, init_pts, batch_inds, conds,
+                                       dthreshold, athreshold, w1, w2, times, return_counters)
     _need_cuda(rays, init_pts)
     dev = init_pts.device
     P = init_pts.shape[0]
@@ -542,7 +549,7 @@ def tc_pack_rows(x):
     lib = _lib.load()
     buf = torch.empty((lib.sr_tc_act_bytes(M, K),), dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):
-        check(lib.sr_tc_pack_rows(_p(x), M, K, K, _p(buf), _stream()), "tc_pack_rows")
+        check(lib.sr_tc_pack_rows(_p(x), M, K, K, _p(buf), None, _stream()), "tc_pack_rows")
     return buf
 
 
@@ -573,7 +580,8 @@ def tc_linear(A, W, bias, M, N, K, n_valid, act, ch=1, K_next=0, scale=1.0, skip
         check(lib.sr_tc_linear(_p(A), _p(W), _p(b), M, N, K, n_valid, int(act), int(ch), _p(A_next),
                                int(K_next), float(scale), _p(skip_src), int(skip_n),
                                skip_src.shape[1] if skip_src is not None else 0, _p(out),
-                               n_valid if want_out else 0, _p(ds), _stream()), "tc_linear")
+                               n_valid if want_out else 0, 0, n_valid, _p(ds), None, 0, None, _stream()),
+              "tc_linear")
     return A_next, out, ds
 
 
@@ -588,6 +596,9 @@ class TcNet:
         lib = _lib.load()
         dev = fused.device
         wbs = [b for b in fused.bufs]
+        parent = getattr(fused, "_parent", None)  # truncated views share the parent's buffers
+        if parent is not None:
+            wbs += [b for b in parent.bufs]
         for i in range(d.n_layers):
             ly = d.layer[i]
             n, k = ly.n, ly.k
@@ -599,7 +610,13 @@ class TcNet:
             npad = _pad(n, 256)
             b = torch.zeros((npad,), dtype=torch.float32, device=dev)
             b[:n] = bias[:n]
-            self.layers.append(dict(W=W, bias=b, n=n, k=k, act=ly.act, skip=bool(ly.skip)))
+            # reverse sweep operand: W_l^T as [k rows][n cols] = the FFMA engine's W_T copy (ld = npad)
+            wt = [t for t in wbs if t is not None and t.data_ptr() == ly.wt][0]
+            Wb = torch.empty((lib.sr_tc_weight_bytes(k, n),), dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                check(lib.sr_tc_pack_weights(_p(wt), k, n, wt.shape[1], _p(Wb), _stream()), "tc_pack_weights")
+            self.layers.append(dict(W=W, Wb=Wb, bias=b, n=n, k=k, act=ly.act, skip=bool(ly.skip),
+                                    zero_bias=torch.zeros((_pad(k, 256),), dtype=torch.float32, device=dev)))
 
 
 def tc_net(fused):
@@ -630,9 +647,9 @@ def tc_mlp_forward(fused, pts, ch=1, conds=None, batch_inds=None, pts_per_frame=
     cd = conds.detach().contiguous().float() if conds is not None else None
     with torch.cuda.device(dev):
         check(lib.sr_tc_embed(_p(pts), P, d.multires, pw, ch, _p(cd), _p(bi), int(pts_per_frame), condlen,
-                              _p(emb), ld, _stream()), "tc_embed")
+                              _p(emb), ld, None, None, _stream()), "tc_embed")
         A = torch.empty((lib.sr_tc_act_bytes(M, ld),), dtype=torch.uint8, device=dev)
-        check(lib.sr_tc_pack_rows(_p(emb), M, ld, ld, _p(A), _stream()), "tc_pack_rows")
+        check(lib.sr_tc_pack_rows(_p(emb), M, ld, ld, _p(A), None, _stream()), "tc_pack_rows")
         K = ld
         out = None
         stashes = []
@@ -650,8 +667,157 @@ def tc_mlp_forward(fused, pts, ch=1, conds=None, batch_inds=None, pts_per_frame=
             check(lib.sr_tc_linear(_p(A), _p(ly["W"]), _p(ly["bias"]), M, ly["n"], K, nv, ly["act"], ch,
                                    _p(A_next), Kn, 0.7071067811865476 if skip_next else 1.0,
                                    _p(emb) if skip_next else None, d.d_in if skip_next else 0, ld, _p(o),
-                                   nv if last else 0, _p(ds), _stream()), "tc_linear")
+                                   nv if last else 0, 0, nv, _p(ds), None, 0, None, _stream()), "tc_linear")
             if ds is not None:
                 stashes.append(ds)
             A, K, out = A_next, Kn, o
     return (out, stashes) if want_dstash else out
+
+
+class _TcTraceBuffers:
+    """Work buffers of the tensor-core tracer, sized by the ray count and cached per device."""
+
+    def __init__(self, dev, P, sdf_net, def_net):
+        lib = _lib.load()
+        self.P = P
+        f32 = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        u8 = lambda n: torch.empty((n,), dtype=torch.uint8, device=dev)
+        self.ld_s = _pad(sdf_net.desc.d_in, 32)
+        self.emb_s = f32(P, self.ld_s)
+        self.A = [u8(lib.sr_tc_act_bytes(P, 512)) for _ in range(2)]
+        self.f = f32(P, 1)
+        self.ds_s = [f32(P, _pad(sdf_net.desc.layer[i].n, 256)) for i in range(sdf_net.desc.n_layers - 1)]
+        self.cot_s = f32(P, 32)
+        self.cot_d = f32(P, 32)
+        self.aux = f32(P, 8)
+        self.gs = f32(P, 64)
+        self.gskip = f32(P, 64)
+        if def_net is not None:
+            self.ld_d = _pad(def_net.desc.d_in, 32)
+            self.emb_d = f32(P, self.ld_d)
+            self.off = f32(P, 3)
+            self.ds_d = [f32(P, _pad(def_net.desc.layer[i].n, 256)) for i in range(def_net.desc.n_layers - 1)]
+            self.gd = f32(P, 64)
+
+
+_tc_trace_bufs = {}
+
+
+def _tc_forward_sweep(lib, net, tcn, emb, ld, A_bufs, P, m_dev, out, stashes):
+    """embedded input (already in `emb`) -> all layers; last layer -> `out` fp32 [P][n_last]."""
+    d = net.desc
+    check(lib.sr_tc_pack_rows(_p(emb), P, ld, ld, _p(A_bufs[0]), _p(m_dev), _stream()), "tc_pack_rows")
+    K = ld
+    cur = 0
+    L = len(tcn.layers)
+    for i, ly in enumerate(tcn.layers):
+        last = i == L - 1
+        nxt = tcn.layers[i + 1] if not last else None
+        Kn = _pad(nxt["k"], 32) if nxt else 0
+        skip_next = bool(nxt and nxt["skip"])
+        check(lib.sr_tc_linear(_p(A_bufs[cur]), _p(ly["W"]), _p(ly["bias"]), P, ly["n"], K, ly["n"], ly["act"], 1,
+                               _p(A_bufs[1 - cur]) if nxt else None, Kn,
+                               0.7071067811865476 if skip_next else 1.0, _p(emb) if skip_next else None,
+                               d.d_in if skip_next else 0, ld, _p(out) if last else None,
+                               out.shape[1] if last else 0, 0, ly["n"] if last else 0,
+                               _p(stashes[i]) if not last else None, None, 0, _p(m_dev), _stream()), "tc_linear")
+        cur, K = 1 - cur, Kn
+
+
+def _tc_backward_sweep(lib, net, tcn, cot, A_bufs, P, m_dev, stashes, g_out, g_skip, n_keep):
+    """cotangent rows `cot` [P][32] of the net outputs -> d/d(embedded input) in g_out [P][ld]
+    (first n_keep columns), skip-connection part in g_skip."""
+    d = net.desc
+    L = len(tcn.layers)
+    check(lib.sr_tc_pack_rows(_p(cot), P, 32, 32, _p(A_bufs[0]), _p(m_dev), _stream()), "tc_pack_rows")
+    cur = 0
+    K = 32
+    for l in range(L - 1, -1, -1):
+        ly = tcn.layers[l]
+        n_prev = tcn.layers[l - 1]["n"] if l > 0 else 0
+        scale = 0.7071067811865476 if ly["skip"] else 1.0
+        if l > 0:
+            Kn = _pad(n_prev, 32)
+            want_skip = ly["skip"]
+            check(lib.sr_tc_linear(_p(A_bufs[cur]), _p(ly["Wb"]), _p(ly["zero_bias"]), P, ly["k"], K, n_prev, 0, 1,
+                                   _p(A_bufs[1 - cur]), Kn, scale, None, 0, 0,
+                                   _p(g_skip) if want_skip else None, g_skip.shape[1] if want_skip else 0,
+                                   n_prev, d.d_in if want_skip else 0, None, _p(stashes[l - 1]),
+                                   stashes[l - 1].shape[1], _p(m_dev), _stream()), "tc_linear")
+            cur, K = 1 - cur, Kn
+        else:
+            check(lib.sr_tc_linear(_p(A_bufs[cur]), _p(ly["Wb"]), _p(ly["zero_bias"]), P, ly["k"], K, ly["k"], 0, 1,
+                                   None, 0, scale, None, 0, 0, _p(g_out), g_out.shape[1], 0, n_keep, None,
+                                   None, 0, _p(m_dev), _stream()), "tc_linear")
+
+
+def trace_surface_points_tc(sdf_net, def_net, lbs, cam_pos, rays, init_pts, batch_inds, conds,
+                            dthreshold=5e-5, athreshold=0.02, w1=3.05, w2=1.0, times=5,
+                            return_counters=False):
+    """OptimizeSurfacePs with the dense layers on the tensor-core engine (reverse-mode sweeps).
+    Same contract as trace_surface_points."""
+    _need_cuda(rays, init_pts)
+    dev = init_pts.device
+    P = init_pts.shape[0]
+    pts = init_pts.detach().contiguous().float().clone()
+    rays = rays.detach().contiguous().float()
+    bi = batch_inds.contiguous().to(torch.int64) if batch_inds is not None else None
+    conds = conds.detach().contiguous().float() if conds is not None else None
+    condlen = conds.shape[-1] if conds is not None else 0
+    conv = torch.zeros((P,), dtype=torch.bool, device=dev)
+    counters = torch.zeros((times + 3,), dtype=torch.int32, device=dev)
+    if P == 0:
+        return (pts, conv, counters) if return_counters else (pts, conv)
+    lib = _lib.load()
+    key = (dev.index, P, id(sdf_net), id(def_net))
+    B = _tc_trace_bufs.get(key)
+    if B is None:
+        _tc_trace_bufs.clear()
+        B = _TcTraceBuffers(dev, P, sdf_net, def_net)
+        _tc_trace_bufs[key] = B
+    ts, td = tc_net(sdf_net), (tc_net(def_net) if def_net is not None else None)
+    lists = [torch.empty((P,), dtype=torch.int32, device=dev) for _ in range(2)]
+    tp = TraceParams()
+    cp = [float(x) for x in cam_pos.detach().view(-1).tolist()]
+    for i in range(3):
+        tp.cam_pos[i] = cp[i]
+    tp.dthreshold, tp.athreshold, tp.w1, tp.w2 = float(dthreshold), float(athreshold), float(w1), float(w2)
+    ds, dd = sdf_net.desc, (def_net.desc if def_net is not None else None)
+    pw_s = (C.c_float * 16)(*[ds.pe_w[i] for i in range(16)])
+    pw_d = (C.c_float * 16)(*[dd.pe_w[i] for i in range(16)]) if dd is not None else None
+    with torch.cuda.device(dev):
+        counters[0] = P
+        for it in range(times + 1):
+            idx = lists[(it + 1) & 1] if it > 0 else None
+            a_out = lists[it & 1] if it < times else None
+            m_dev = counters[it:it + 1]
+            # ---- forward sweeps (act' stashed when an update follows)
+            check(lib.sr_tc_embed(_p(pts), P, ds.multires, pw_s, 1, None, None, 0, 0, _p(B.emb_s), B.ld_s,
+                                  _p(idx), _p(m_dev), _stream()), "tc_embed")
+            _tc_forward_sweep(lib, sdf_net, ts, B.emb_s, B.ld_s, B.A, P, m_dev, B.f, B.ds_s)
+            if def_net is not None:
+                check(lib.sr_tc_embed(_p(pts), P, dd.multires, pw_d, 1, _p(conds), _p(bi), 0, condlen,
+                                      _p(B.emb_d), B.ld_d, _p(idx), _p(m_dev), _stream()), "tc_embed")
+                _tc_forward_sweep(lib, def_net, td, B.emb_d, B.ld_d, B.A, P, m_dev, B.off, B.ds_d)
+            check(lib.sr_tc_trace_mid(_p(idx), _p(m_dev), P, _p(pts), _p(rays), _p(bi), _p(B.f),
+                                      _p(B.off) if def_net is not None else None, _lbs_ref(lbs), C.byref(tp),
+                                      1 if a_out is not None else 0, _p(conv), _p(B.cot_s),
+                                      _p(B.cot_d) if def_net is not None else None, 32, _p(B.aux), _stream()),
+                  "tc_trace_mid")
+            if a_out is None:
+                break
+            # ---- reverse sweeps + update
+            _tc_backward_sweep(lib, sdf_net, ts, B.cot_s, B.A, P, m_dev, B.ds_s, B.gs, B.gskip, ds.d_in)
+            if def_net is not None:
+                _tc_backward_sweep(lib, def_net, td, B.cot_d, B.A, P, m_dev, B.ds_d, B.gd, B.gskip,
+                                   3 + 6 * dd.multires)
+            has_skip = any(l["skip"] for l in ts.layers)
+            check(lib.sr_tc_trace_update(_p(idx), _p(m_dev), P, _p(pts), _p(B.gs), B.gs.shape[1],
+                                         _p(B.gskip) if has_skip else None, B.gskip.shape[1],
+                                         _p(B.gd) if def_net is not None else None,
+                                         B.gd.shape[1] if def_net is not None else 0, _p(B.aux), ds.multires,
+                                         pw_s, dd.multires if dd is not None else 0, pw_d, _p(a_out),
+                                         _p(counters[it + 1:it + 2]), _stream()), "tc_trace_update")
+    if return_counters:
+        return pts, conv, counters
+    return pts, conv
