@@ -135,8 +135,11 @@ def ray_part(sc, rays, init, bi, stats=None):
                                                    5e-5, sc["ang"], 3.05, 1.0, 10, return_counters=True)
     full = sdf.fused()
     full.set_pe_weights([1.0] * 6)
-    n, cr, feat, _, _ = ops.shade_geometry(full, dnet, lbs, pts, rays, bi, sc["conds"][0], nfeat=256)
-    rgb = ops.render_forward(rn.fused(RATIO), pts, n, cr, feat)
+    if ops.TC_ENABLED and pts.shape[0] >= ops.TC_MIN_POINTS:
+        n, cr, rgb, _, _ = ops.shade_and_render_tc(full, dnet, lbs, rn.fused(RATIO), pts, rays, bi, sc["conds"][0])
+    else:
+        n, cr, feat, _, _ = ops.shade_geometry(full, dnet, lbs, pts, rays, bi, sc["conds"][0], nfeat=256)
+        rgb = ops.render_forward(rn.fused(RATIO), pts, n, cr, feat)
     if stats is not None:
         stats["counters"] = counters
     return pts, conv, rgb

@@ -306,6 +306,18 @@ int sr_tc_trace_update(const int32_t* index, const int32_t* m_dev, int64_t P, fl
                        int gd_ld, const float* aux, int mr_s, const float* pw_s, int mr_d,
                        const float* pw_d, int32_t* active_out, int32_t* counter_out, cudaStream_t s);
 
+/* Shading on the tensor-core engine: sr_tc_shade_point turns the 4-rows-per-point outputs of the
+ * SDF (value / grad f in column 0) and translator (offset / d offset) sweeps into normals,
+ * cardinal rays (J^-1 v, fallback v when |det J| < 1e-4) and D(p); sr_tc_render_embed builds
+ * cat([p, PE(view), n, feat]) rows for the rendering network (RenderNet.py:73-74); feat is read
+ * from row p*feat_row_stride of a [*, feat_ld] matrix starting at column feat_col0. */
+int sr_tc_shade_point(int64_t P, const float* pts, const float* rays, const int64_t* batch_inds,
+                      const float* sdf4, int ld_s, const float* off4, const sr_lbs_params* lbs,
+                      float* normals, float* crays, float* dpos, uint8_t* inv_ok, cudaStream_t s);
+int sr_tc_render_embed(int64_t P, const float* pts, const float* views, const float* normals,
+                       const float* feat, int feat_ld, int feat_col0, int nfeat, int feat_row_stride,
+                       int multires, const float* pw, float* out, int ld, cudaStream_t s);
+
 /* ------------------------------------------------------------------------------------------
  * Coarse-to-fine SDF grid plumbing (Seg3dLossless, MCAcc/seg3d_lossless.py:266-372).
  *   cand[z,y,x] = any(flag over the zero-padded 3x3x3 neighbourhood)

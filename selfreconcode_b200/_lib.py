@@ -103,6 +103,10 @@ SIGNATURES = {
                                   C.POINTER(TraceParams), i32, c_f, c_f, c_f, i32, c_f, stream_t]),
     "sr_tc_trace_update": (C.c_int, [c_f, c_f, i64, c_f, c_f, i32, c_f, i32, c_f, i32, c_f, i32,
                                      C.POINTER(f32), i32, C.POINTER(f32), c_f, c_f, stream_t]),
+    "sr_tc_shade_point": (C.c_int, [i64, c_f, c_f, c_f, c_f, i32, c_f, C.POINTER(LbsParams), c_f, c_f, c_f,
+                                    c_f, stream_t]),
+    "sr_tc_render_embed": (C.c_int, [i64, c_f, c_f, c_f, c_f, i32, i32, i32, i32, i32, C.POINTER(f32), c_f,
+                                     i32, stream_t]),
     "sr_seg3d_candidates": (C.c_int, [c_f, c_f, c_f, i32, i32, i32, i32, i32, i32, i32, i32, i32,
                                       stream_t]),
 }

@@ -158,9 +158,147 @@ __global__ void __launch_bounds__(256) trace_update_kernel(const __grid_constant
   }
 }
 
+// ---- shading geometry from the tensor-core engine's outputs (infer path, network.py:356-361;
+//      utils/utils.py:155-169): one warp per ray.
+struct ShadePtArgs {
+  long long P;
+  const float* pts;
+  const float* rays;
+  const long long* batch_inds;
+  const float* sdf4;   // [P*4][ld_s]: col 0 of rows 4p+1..4p+3 = grad f
+  int ld_s;
+  const float* off4;   // [P*4][3] translator offset (row 4p) and its tangents (rows 4p+1..3), or null
+  sr_lbs_params lbs;
+  int has_lbs;
+  float* normals;
+  float* crays;
+  float* dpos;
+  unsigned char* inv_ok;
+};
+
+__global__ void __launch_bounds__(256) shade_point_kernel(const __grid_constant__ ShadePtArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long i = warp0; i < a.P; i += nwarps) {
+    float p[3], pp[3], off[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      p[j] = a.pts[i * 3 + j];
+      if (a.off4) off[j] = a.off4[(i * 4) * 3 + j];
+      pp[j] = __fadd_rn(p[j], off[j]);
+    }
+    float d[3], Mm[9];
+    int ci[3];
+    if (a.has_lbs) lbs_point(a.lbs, pp, a.batch_inds ? (int)a.batch_inds[i] : 0, d, Mm, ci);
+    else {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) d[j] = pp[j];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) Mm[q] = (q % 4 == 0) ? 1.f : 0.f;
+    }
+    if (lane == 0) {
+      // J = M (I + Joff), Joff[m][c] = d off_m / d p_c = off4[4i+1+c][m]
+      float Q[9], m[9];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Q[3 * r + c] = (r == c ? 1.f : 0.f) + (a.off4 ? a.off4[(i * 4 + 1 + c) * 3 + r] : 0.f);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) m[3 * r + c] = Mm[3 * r] * Q[c] + Mm[3 * r + 1] * Q[3 + c] + Mm[3 * r + 2] * Q[6 + c];
+      const float gx = a.sdf4[(i * 4 + 1) * a.ld_s], gy = a.sdf4[(i * 4 + 2) * a.ld_s], gz = a.sdf4[(i * 4 + 3) * a.ld_s];
+      const float gn = sqrtf(gx * gx + gy * gy + gz * gz);
+      a.normals[i * 3] = gx / gn; a.normals[i * 3 + 1] = gy / gn; a.normals[i * 3 + 2] = gz / gn;
+      const float c00 = m[4] * m[8] - m[5] * m[7], c01 = -m[3] * m[8] + m[5] * m[6], c02 = m[3] * m[7] - m[4] * m[6];
+      const float c10 = -m[1] * m[8] + m[2] * m[7], c11 = m[0] * m[8] - m[2] * m[6], c12 = -m[0] * m[7] + m[1] * m[6];
+      const float c20 = m[1] * m[5] - m[2] * m[4], c21 = -m[0] * m[5] + m[2] * m[3], c22 = m[0] * m[4] - m[1] * m[3];
+      const float det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+      const bool ok = !(fabs((double)det) < 0.0001);
+      const float vx = a.rays[i * 3], vy = a.rays[i * 3 + 1], vz = a.rays[i * 3 + 2];
+      float rx = vx, ry = vy, rz = vz;
+      if (ok) {
+        rx = (c00 / det) * vx + (c10 / det) * vy + (c20 / det) * vz;
+        ry = (c01 / det) * vx + (c11 / det) * vy + (c21 / det) * vz;
+        rz = (c02 / det) * vx + (c12 / det) * vy + (c22 / det) * vz;
+      }
+      const float rn = sqrtf(rx * rx + ry * ry + rz * rz);
+      a.crays[i * 3] = rx / rn; a.crays[i * 3 + 1] = ry / rn; a.crays[i * 3 + 2] = rz / rn;
+      if (a.dpos) { a.dpos[i * 3] = d[0]; a.dpos[i * 3 + 1] = d[1]; a.dpos[i * 3 + 2] = d[2]; }
+      if (a.inv_ok) a.inv_ok[i] = ok ? 1 : 0;
+    }
+  }
+}
+
+// rendering_input = cat([points, PE(view_dirs), normals, feature_vectors]) (RenderNet.py:73-74)
+struct RenderEmbedArgs {
+  long long P;
+  const float* pts;
+  const float* views;
+  const float* normals;
+  const float* feat;   // [P][feat_ld], first nfeat columns used (starting at feat_col0)
+  int feat_ld, feat_col0, nfeat, feat_row_stride;
+  int multires;
+  float pw[16];
+  float* out;
+  int ld;
+};
+__global__ void render_embed_kernel(const __grid_constant__ RenderEmbedArgs a) {
+  const long long total = a.P * (long long)a.ld;
+  const int pe = 3 + 6 * a.multires;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % a.ld);
+    const long long p = idx / a.ld;
+    float v = 0.f;
+    if (k < 3) v = a.pts[p * 3 + k];
+    else if (k < 3 + pe) {
+      const int q = k - 3;
+      if (q < 3) v = a.views[p * 3 + q];
+      else {
+        const int b = (q - 3) / 6, w6 = (q - 3) % 6, j = w6 % 3;
+        float sn, cs;
+        sincosf(a.views[p * 3 + j] * (float)(1 << b), &sn, &cs);
+        v = a.pw[b] * (w6 >= 3 ? cs : sn);
+      }
+    } else if (k < 3 + pe + 3) v = a.normals[p * 3 + (k - 3 - pe)];
+    else if (k < 3 + pe + 3 + a.nfeat)
+      v = a.feat[(size_t)p * a.feat_row_stride * a.feat_ld + a.feat_col0 + (k - 3 - pe - 3)];
+    a.out[idx] = v;
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int sr_tc_shade_point(int64_t P, const float* pts, const float* rays, const int64_t* batch_inds,
+                      const float* sdf4, int ld_s, const float* off4, const sr_lbs_params* lbs,
+                      float* normals, float* crays, float* dpos, uint8_t* inv_ok, cudaStream_t s) {
+  if (P <= 0 || !pts || !rays || !sdf4 || !normals || !crays) return SR_EINVAL;
+  ShadePtArgs a;
+  a.P = P; a.pts = pts; a.rays = rays; a.batch_inds = (const long long*)batch_inds; a.sdf4 = sdf4;
+  a.ld_s = ld_s; a.off4 = off4; a.has_lbs = lbs ? 1 : 0;
+  if (lbs) a.lbs = *lbs;
+  a.normals = normals; a.crays = crays; a.dpos = dpos; a.inv_ok = inv_ok;
+  shade_point_kernel<<<sr_grid_for(P * 32, 256, 8), 256, 0, s>>>(a);
+  return sr_launch_status();
+}
+
+int sr_tc_render_embed(int64_t P, const float* pts, const float* views, const float* normals,
+                       const float* feat, int feat_ld, int feat_col0, int nfeat, int feat_row_stride,
+                       int multires, const float* pw, float* out, int ld, cudaStream_t s) {
+  if (P <= 0 || !pts || !views || !normals || !out || !pw || (nfeat > 0 && !feat)) return SR_EINVAL;
+  if (ld < 3 + 3 + 6 * multires + 3 + nfeat) return SR_EINVAL;
+  RenderEmbedArgs a;
+  a.P = P; a.pts = pts; a.views = views; a.normals = normals; a.feat = feat; a.feat_ld = feat_ld;
+  a.feat_col0 = feat_col0; a.nfeat = nfeat; a.feat_row_stride = feat_row_stride; a.multires = multires;
+  for (int i = 0; i < 16; ++i) a.pw[i] = i < multires ? pw[i] : 0.f;
+  a.out = out; a.ld = ld;
+  render_embed_kernel<<<sr_grid_for(P * (long long)ld, 256, 8), 256, 0, s>>>(a);
+  return sr_launch_status();
+}
 
 int sr_tc_trace_mid(const int32_t* index, const int32_t* m_dev, int64_t P, const float* pts,
                     const float* rays, const int64_t* batch_inds, const float* f, const float* off,

@@ -821,3 +821,57 @@ def trace_surface_points_tc(sdf_net, def_net, lbs, cam_pos, rays, init_pts, batc
     if return_counters:
         return pts, conv, counters
     return pts, conv
+
+
+def _tc_layers_from_rows(lib, tcn, d_in, emb, ld, M, ch, n_out_last=None, skip_emb=None):
+    """embedded rows fp32 [M][ld] -> last layer outputs fp32 [M][n_last] on the tensor-core engine."""
+    dev = emb.device
+    A = torch.empty((lib.sr_tc_act_bytes(M, ld),), dtype=torch.uint8, device=dev)
+    check(lib.sr_tc_pack_rows(_p(emb), M, ld, ld, _p(A), None, _stream()), "tc_pack_rows")
+    K = ld
+    out = None
+    L = len(tcn.layers)
+    for i, ly in enumerate(tcn.layers):
+        last = i == L - 1
+        nxt = tcn.layers[i + 1] if not last else None
+        nv = ly["n"] if not (last and n_out_last) else n_out_last
+        Kn = _pad(nxt["k"], 32) if nxt else 0
+        skip_next = bool(nxt and nxt["skip"])
+        A_next = torch.empty((lib.sr_tc_act_bytes(M, Kn),), dtype=torch.uint8, device=dev) if nxt else None
+        o = torch.empty((M, nv), dtype=torch.float32, device=dev) if last else None
+        check(lib.sr_tc_linear(_p(A), _p(ly["W"]), _p(ly["bias"]), M, ly["n"], K, nv, ly["act"], ch, _p(A_next), Kn,
+                               0.7071067811865476 if skip_next else 1.0, _p(emb) if skip_next else None,
+                               d_in if skip_next else 0, ld, _p(o), nv if last else 0, 0, nv, None, None, 0,
+                               None, _stream()), "tc_linear")
+        A, K, out = A_next, Kn, o
+    return out
+
+
+def shade_and_render_tc(sdf_full, def_net, lbs, render_net, pts, rays, batch_inds, conds, nfeat=256):
+    """Shading of the infer path on the tensor-core engine: SDF and translator sweeps with forward
+    tangents (4 rows per point), pointwise geometry, then the rendering network.
+    Returns (normals, cardinal rays, rgb, D(p), inverse-ok mask)."""
+    _need_cuda(pts, rays)
+    dev = pts.device
+    P = pts.shape[0]
+    pts = pts.detach().contiguous().float()
+    rays = rays.detach().contiguous().float()
+    bi = batch_inds.contiguous().to(torch.int64) if batch_inds is not None else None
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        s4 = tc_mlp_forward(sdf_full, pts, ch=4)                      # [4P, 1+nfeat]
+        o4 = tc_mlp_forward(def_net, pts, ch=4, conds=conds, batch_inds=bi) if def_net is not None else None
+        normals = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        crays = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        dpos = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        ok = torch.empty((P,), dtype=torch.bool, device=dev)
+        check(lib.sr_tc_shade_point(P, _p(pts), _p(rays), _p(bi), _p(s4), s4.shape[1], _p(o4), _lbs_ref(lbs),
+                                    _p(normals), _p(crays), _p(dpos), _p(ok), _stream()), "tc_shade_point")
+        rd = render_net.desc
+        ld = _pad(rd.d_in, 32)
+        emb = torch.empty((P, ld), dtype=torch.float32, device=dev)
+        pw = (C.c_float * 16)(*[rd.pe_w[i] for i in range(16)])
+        check(lib.sr_tc_render_embed(P, _p(pts), _p(crays), _p(normals), _p(s4), s4.shape[1], 1, nfeat, 4,
+                                     rd.multires, pw, _p(emb), ld, _stream()), "tc_render_embed")
+        rgb = _tc_layers_from_rows(lib, tc_net(render_net), rd.d_in, emb, ld, P, 1)
+    return normals, crays, rgb, dpos, ok

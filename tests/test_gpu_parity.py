@@ -567,3 +567,25 @@ def test_tc_mlp_matches_ffma_engine_and_golden(cuda_dev):
     dc = torch.from_numpy(gd["dcond"]).to(cuda_dev)
     off = ops.tc_mlp_forward(tr.fused(RATIO), p2, ch=1, conds=dc, batch_inds=bi)
     assert rel_err(off.cpu().numpy(), gd["offset"]) < FP_TOL
+
+
+def test_tc_shade_and_render_match_ffma_engine(cuda_dev):
+    from selfreconcode_b200 import ops
+    g, c, gs, gr = golden("deform.npz"), golden("cardinal.npz"), golden("sdf_full.npz"), golden("render.npz")
+    comp, conds = _deform_modules(g, cuda_dev)
+    sdf = build_sdf_full(gs).to(cuda_dev)
+    rn = build_render(gr).to(cuda_dev)
+    pts = torch.from_numpy(g["pts"]).to(cuda_dev)
+    bi = torch.from_numpy(g["batch_inds"]).to(cuda_dev)
+    rays = torch.from_numpy(c["rays"]).to(cuda_dev)
+    lbs = comp.defs[1].lbs_state()
+    lbs.set_pose(conds[1][0], conds[1][1])
+    full, dnet, rnet = sdf.fused(), comp.defs[0].fused(RATIO), rn.fused(RATIO)
+    n, cr, rgb, dp, ok = ops.shade_and_render_tc(full, dnet, lbs, rnet, pts, rays, bi, conds[0])
+    assert rel_err(cr.cpu().numpy(), c["crays"]) < FP_TOL            # reference (golden)
+    assert rel_err(dp.cpu().numpy(), c["ds"]) < FP_TOL
+    n2, cr2, ft, _, _ = ops.shade_geometry(full, dnet, lbs, pts, rays, bi, conds[0], nfeat=256)
+    rgb2 = ops.render_forward(rnet, pts, n2, cr2, ft)
+    assert rel_err(n.cpu().numpy(), n2.cpu().numpy()) < FP_TOL
+    assert rel_err(rgb.cpu().numpy(), rgb2.cpu().numpy()) < 2 * FP_TOL
+    assert ok.all()
