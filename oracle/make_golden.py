@@ -13,6 +13,7 @@ checksum before using them.
 """
 import os
 import sys
+import types
 
 import numpy as np
 import torch
@@ -57,6 +58,14 @@ def synth_ws(D, H, W, bmin, bmax, Js, sigma=0.25):
              ((xs - Js[j, 0]) ** 2).view(1, 1, W)
         logits[j] = -d2 / (2 * sigma * sigma)
     return torch.softmax(logits, 0).unsqueeze(0).contiguous()
+
+
+def grad_digest(grad, idx):
+    """[norm, dot with a seeded gaussian, <=128 strided samples] of a gradient tensor."""
+    flat = grad.detach().double().reshape(-1)
+    r = torch.randn(flat.numel(), generator=torch.Generator().manual_seed(9000 + idx), dtype=torch.float64)
+    stride = max(1, flat.numel() // 128)
+    return np.concatenate([[flat.norm().item(), (flat * r).sum().item()], flat[::stride][:128].numpy()])
 
 
 def pack_grid(grid, queried):
@@ -207,6 +216,77 @@ def main():
             res["f_" + name] = sdf_full(out_p, RATIO).view(-1).numpy()
     np.savez(os.path.join(OUT, "trace.npz"), rays=v.numpy(), start=start.numpy(),
              batch_inds=bi2.numpy(), cam_pos=cam_pos.numpy(), athreshold=0.0112, **res)
+
+    # ---------------------------------------------------------------- propagateTmpPsGrad
+    # OptimNetwork.propagateTmpPsGrad (network.py:702-814) run by the reference itself on fake
+    # dataset / renderer holders; the camera is the reference's RectifiedPerspectiveCameras with the
+    # pytorch3d base-class constructor bypassed (its view_rays / cam_pos / angThreshold are used).
+    import model.CameraMine as ref_cam
+
+    class GoldCam(ref_cam.RectifiedPerspectiveCameras):
+        def __init__(self, focal_length, principal_point, R, T, image_size=None, **kw):
+            self.focal_length, self.principal_point, self.R, self.T = focal_length, principal_point, R, T
+            self.image_size = torch.tensor(image_size)
+
+        def to(self, device):
+            return self
+
+    net_mod.RectifiedPerspectiveCameras = GoldCam
+    g = torch.Generator().manual_seed(71)
+    Hh = Ww = 64
+    focals0 = torch.tensor([[150.0, 152.0]]).repeat(N, 1)
+    pps0 = torch.tensor([[31.5, 32.5]]).repeat(N, 1)
+    Rs0 = torch.tensor([[[-1., 0., 0.], [0., 1., 0.], [0., 0., -1.]]]).repeat(N, 1, 1)
+    Ts0 = torch.tensor([[0.02, -0.01, 2.5]]).repeat(N, 1)
+    cam0 = GoldCam(focals0, pps0, Rs0, Ts0, image_size=[(Ww, Hh)])
+    Pg = 40
+    with torch.no_grad():
+        dg = comp(pstar[:Pg], [dcond, [poses, trans]], bi2[:Pg], ratio=RATIO)
+        pix = cam0.project(dg)
+    col = pix[:, 0].round().long()
+    row = pix[:, 1].round().long()
+    tmpps = pstar[:Pg] + 2e-3 * torch.randn(Pg, 3, generator=g)
+    gl = torch.randn(Pg, 3, generator=g)
+    out = dict(col=col.numpy(), row=row.numpy(), batch_inds=bi2[:Pg].numpy(), tmpps=tmpps.numpy(),
+               grad_l_p=gl.numpy(), focals=focals0.numpy(), pps=pps0.numpy(), Rs=Rs0.numpy(), Ts=Ts0.numpy(),
+               H=Hh, W=Ww, angthr=cam0.angThreshold(0.5))
+    for case in ("fixedcam", "optcam"):
+        opt = case == "optcam"
+        cam_t = [t.clone().requires_grad_(opt) for t in (focals0, pps0, Rs0, Ts0)]
+        cond_t = [t.clone().requires_grad_(True) for t in (poses, trans, dcond)]
+
+        class FakeData:
+            def get_grad_parameters(self, fids, device):
+                return cond_t[0], cond_t[1], cond_t[2], None
+
+            def get_camera_parameters(self, n, device):
+                return cam_t[0], cam_t[1], cam_t[2], cam_t[3], Hh, Ww
+
+        holder = types.SimpleNamespace(rasterizer=types.SimpleNamespace(cameras=cam0))
+        sdf_full.zero_grad()
+        comp.zero_grad()
+        on = net_mod.OptimNetwork(sdf_full, comp, None, holder, None, conf=None)
+        on.dataset = FakeData()
+        on.info = {}
+        on.TmpPs = tmpps.clone().requires_grad_(True)
+        on.TmpPs.grad = gl.clone()
+        camg = GoldCam(*cam_t, image_size=[(Ww, Hh)])
+        pixh = torch.cat([col.view(-1, 1), row.view(-1, 1), torch.ones_like(col.view(-1, 1))], dim=-1).float()
+        on.rays = camg.view_rays(pixh)
+        on.col_inds, on.row_inds, on.batch_inds = col, row, bi2[:Pg]
+        on.propagateTmpPsGrad(torch.arange(N), RATIO)
+        out[case + "_invinfo"] = np.array(on.info['invInfo'])
+        out[case + "_rays"] = on.rays.detach().numpy()
+        named = [("sdf." + k, q) for k, q in sorted(sdf_full.named_parameters())] + \
+                [("def." + k, q) for k, q in sorted(comp.named_parameters())] + \
+                list(zip(("poses", "trans", "dcond"), cond_t))
+        if opt:
+            named += list(zip(("focals", "pps", "Rs", "Ts"), cam_t))
+        for i, (k, q) in enumerate(named):
+            if q.grad is None:
+                continue
+            out[case + "__" + k] = grad_digest(q.grad, i)
+    np.savez(os.path.join(OUT, "propagate.npz"), **out)
 
     # ---------------------------------------------------------------- Seg3dLossless (reference)
     def query(points):

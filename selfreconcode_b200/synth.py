@@ -205,3 +205,44 @@ def ang_threshold(cam, pixoffset=0.5):
 MC_LADDER_257 = [(33, 33, 33), (65, 65, 65), (129, 129, 129), (257, 257, 257)]
 MC_LADDER_513 = MC_LADDER_257 + [(513, 513, 513)]
 MC_LADDER_65 = [(9, 9, 9), (17, 17, 17), (33, 33, 33), (65, 65, 65)]
+
+
+class Conf(dict):
+    """Tiny stand-in for the pyhocon ConfigTree the reference passes around (config.conf
+    `loss_*` blocks): get_float / get_int / get_bool plus `in`."""
+
+    def get_float(self, k):
+        return float(self[k])
+
+    def get_int(self, k):
+        return int(self[k])
+
+    def get_bool(self, k):
+        return bool(self[k])
+
+
+class SyntheticDataset(torch.nn.Module):
+    """The two accessors the hot path calls on the reference's dataset (dataset/dataset.py
+    get_grad_parameters / get_camera_parameters): per-frame pose / translation / latent codes as
+    learnable parameters plus one shared pinhole camera."""
+
+    def __init__(self, n_frames, H, W, seed=5, condlen=128, rendcondlen=0, learn_camera=False):
+        super().__init__()
+        poses, trans, dcond = make_frame_params(seed, n_frames, condlen)
+        self.poses = torch.nn.Parameter(poses)
+        self.trans = torch.nn.Parameter(trans)
+        self.conds = torch.nn.ParameterList([torch.nn.Parameter(dcond)])
+        cam = camera(H, W)
+        self.H, self.W = H, W
+        self.focals = torch.nn.Parameter(cam["focal"].view(1, 2), requires_grad=learn_camera)
+        self.pps = torch.nn.Parameter(cam["pp"].view(1, 2), requires_grad=learn_camera)
+        self.register_buffer("Rs", cam["R"].view(1, 3, 3))
+        self.Ts = torch.nn.Parameter(cam["T"].view(1, 3), requires_grad=learn_camera)
+
+    def get_grad_parameters(self, frame_ids, device):
+        return (self.poses[frame_ids].to(device), self.trans[frame_ids].to(device),
+                self.conds[0][frame_ids].to(device), None)
+
+    def get_camera_parameters(self, n, device):
+        return (self.focals.expand(n, 2).to(device), self.pps.expand(n, 2).to(device),
+                self.Rs.expand(n, 3, 3).to(device), self.Ts.expand(n, 3).to(device), self.H, self.W)

@@ -1,0 +1,102 @@
+"""One optimisation step through the OptimNetwork drop-in on synthetic data (train.py:150-171's
+sequence: forward -> backward -> propagateTmpPsGrad -> optimizer.step), plus the ray part of
+infer() and discretizeSDF.  Component parity lives in test_gpu_parity / test_optim_propagate; here
+the sequence is checked for self-consistency on the GPU."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def build(n_frames=2, Hh=96, Ww=96):
+    H.dropin()
+    from selfreconcode_b200 import synth
+    from model.Deformer import CompositeDeformer
+    from model.optim import OptimNetwork
+    from model.CameraMine import RectifiedPerspectiveCameras
+    from MCAcc import Seg3dLossless
+    dev = "cuda"
+    sdf = synth.make_sdf().to(dev)
+    comp = CompositeDeformer([synth.make_translator(), synth.make_skinner(resolution=(33, 57, 17))]).to(dev)
+    rn = synth.make_render().to(dev)
+    data = synth.SyntheticDataset(n_frames, Hh, Ww).to(dev)
+    cam = synth.camera(Hh, Ww)
+    fids = torch.arange(n_frames, device=dev)
+    poses, trans, dcond, _ = data.get_grad_parameters(fids, dev)
+    with torch.no_grad():
+        rays = synth.make_rays(cam, n_frames,
+                               lambda p: sdf.forward_fused(p.to(dev), H.RATIO, False, False)[0].view(-1),
+                               lambda p, b: comp.forward_fused(p.to(dev), [dcond, [poses, trans]], b.to(dev), H.RATIO)[0])
+    f, pp, R, T, _, _ = data.get_camera_parameters(n_frames, dev)
+    cams = RectifiedPerspectiveCameras(f.detach(), pp.detach(), R, T.detach(), image_size=[(Ww, Hh)])
+    holder = types.SimpleNamespace(rasterizer=types.SimpleNamespace(cameras=cams))
+    eng = Seg3dLossless(query_func=None, b_min=[[-0.9], [-0.9], [-0.9]], b_max=[[0.9], [0.9], [0.9]],
+                        resolutions=[(9, 9, 9), (17, 17, 17), (33, 33, 33), (65, 65, 65)],
+                        align_corners=False, balance_value=0.0, device=dev, visualize=False, debug=False,
+                        use_cuda_impl=True, faster=False)
+    conf = synth.Conf(grad_weight=0.1, color_weight=0.5, normal_weight=0.0)
+    net = OptimNetwork(sdf, comp, eng, holder, rn, conf=conf)
+    net.dataset = data
+    return net, data, rays, fids
+
+
+def test_training_step_sequence():
+    net, data, rays, fids = build()
+    dev = "cuda"
+    N, Hh, Ww = fids.numel(), data.H, data.W
+    params = list(net.sdf.parameters()) + list(net.deformer.parameters()) + list(net.netRender.parameters()) \
+        + list(data.parameters())
+    opt = torch.optim.Adam([q for q in params if q.requires_grad], lr=1e-4)
+    before = [q.detach().clone() for q in net.sdf.parameters()]
+    img = torch.rand(N, Hh, Ww, 3, device=dev) * 2 - 1
+    # the traced pixel set: aim rays from the pixel grid so that view_rays(pix) is the ray
+    bi, ri, ci = rays["batch_inds"].to(dev), rays["rows"].to(dev), rays["cols"].to(dev)
+    loss = net.forward_rays({"img": img}, bi, ri, ci, rays["pstar"].to(dev), H.RATIO, fids)
+    assert torch.isfinite(loss)
+    total, conv = net.info["rayInfo"]
+    assert total == bi.numel() and conv > 0.5 * total, net.info
+    opt.zero_grad()
+    loss.backward()
+    assert net.TmpPs.grad is not None and float(net.TmpPs.grad.abs().max()) > 0
+    g_before = net.sdf.lin3.weight_v.grad.detach().clone()
+    net.propagateTmpPsGrad(fids, H.RATIO)
+    tot, ok = net.info["invInfo"]
+    assert tot == conv and ok > 0.9 * tot
+    # the implicit-differentiation term reaches the sdf, the translator and the per-frame codes
+    assert float((net.sdf.lin3.weight_v.grad - g_before).abs().max()) > 0
+    assert float(net.deformer.defs[0].lin0.weight.grad.abs().max()) > 0
+    assert float(data.poses.grad.abs().max()) > 0 and float(data.conds[0].grad.abs().max()) > 0
+    for q in params:
+        if q.grad is not None:
+            assert torch.isfinite(q.grad).all()
+    opt.step()
+    assert any(float((a - b).abs().max()) > 0 for a, b in zip(before, net.sdf.parameters()))
+    # folded weights must follow the optimiser step (FoldCache keyed on Tensor._version)
+    p = rays["pstar"][:64].to(dev)
+    with torch.no_grad():
+        fused = net.sdf.forward_fused(p, H.RATIO, False, False)[0].view(-1)
+    plain = net.sdf(p.clone().requires_grad_(True), H.RATIO).view(-1)
+    assert H.rel_err(fused.cpu().numpy(), plain.detach().cpu().numpy()) < 1e-4
+
+
+def test_infer_rays_and_discretize():
+    net, data, rays, fids = build()
+    dev = "cuda"
+    bi, ri, ci = rays["batch_inds"].to(dev), rays["rows"].to(dev), rays["cols"].to(dev)
+    colors = net.infer_rays(bi, ri, ci, rays["init_pts"].to(dev), data.H, data.W, H.RATIO, fids)
+    assert colors.shape == (fids.numel(), data.H, data.W, 3)
+    assert float(colors.min()) >= 0 and float(colors.max()) <= 255
+    bg = torch.ones_like(colors[..., 0], dtype=torch.bool)
+    bg[bi, ri, ci] = False
+    assert float((colors[bg] - 255.).abs().max()) == 0
+    assert float((colors[~bg] - 255.).abs().max()) > 0
+    verts, faces = net.discretizeSDF(H.RATIO, None, 0.0)
+    assert verts.shape[0] > 100 and faces.shape[0] > 100 and int(faces.max()) == verts.shape[0] - 1
+    with torch.no_grad():
+        f = net.sdf.forward_fused(verts, H.RATIO, False, False)[0].view(-1)
+    assert float(f.abs().max()) < 2e-3   # vertices sit on the zero set up to the linear edge interpolation
