@@ -160,11 +160,7 @@ def ray_part_api(sc, rays, init, bi):
     cam_pos = sc["cam"]["cam_pos"].to(rays.device)
     pts, conv = utils.OptimizeSurfacePs(cam_pos, rays, init, bi, sdf, RATIO, comp, sc["conds"], dthreshold=5e-5,
                                         athreshold=sc["ang"], w1=3.05, w2=1., times=10)
-    s, nx, feat = sdf.forward_fused(pts, RATIO, want_grad=True, want_feat=True)
-    nx = nx / nx.norm(dim=1, keepdim=True)
-    crays, dv = utils.compute_cardinal_rays(comp, pts, rays, sc["conds"], bi, RATIO, 'test')
-    with torch.no_grad():
-        rgb = utils.compute_netRender_color(rn, pts, dv, nx, crays, feat, None, RATIO)
+    _, _, rgb = utils.shade_rays(sdf, comp, rn, pts, rays, sc["conds"], bi, RATIO)
     return pts, conv, rgb
 
 

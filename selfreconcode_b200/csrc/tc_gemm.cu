@@ -64,14 +64,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   return d;
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=256
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                            ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t kIdescBase = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BM >> 4) << 24);
 
-__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
@@ -81,18 +81,30 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+#define SR_TMEM_REGS32(v)                                                                          \
+  "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),  \
+  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),          \
+  "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),        \
+  "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),        \
+  "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+#define SR_TMEM_REGS32_RW(v)                                                                       \
+  "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),  \
+  "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]),          \
+  "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]),        \
+  "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]),        \
+  "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+// asynchronous TMEM -> register load of 32 columns (this warp's 32 lanes); pair with tmem_wait
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
       "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
-        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
-        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : SR_TMEM_REGS32(v)
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// the registers are in/out operands so that no consumer can be scheduled above the wait
+__device__ __forceinline__ void tmem_wait(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : SR_TMEM_REGS32_RW(v)::"memory");
 }
 
 struct LayerArgs {
@@ -101,8 +113,8 @@ struct LayerArgs {
   const float* bias;        // [NT*256]
   long long M;              // valid rows
   int MT, NT, KC;           // row tiles, col tiles, k chunks (K = 32*KC)
+  int n_gemm;               // columns the GEMM produces (<= NT*256); the MMA N of the last tile shrinks to it
   int n;                    // valid output columns
-  int act;                  // SR_ACT_*
   int ch;                   // rows per point: 1 (value only) or 4 (value + 3 tangents)
   // outputs (either may be null)
   __nv_bfloat16* A_next;    // tiled, KCn chunks: activations for the next layer
@@ -120,20 +132,147 @@ struct LayerArgs {
   const int* m_dev;         // optional device-side row count (active rays); M is the upper bound
 };
 
-__device__ __forceinline__ float act_fn(int act, float z, float& d) {
-  if (act == SR_ACT_SOFTPLUS100) {
+template <int ACT>
+__device__ __forceinline__ float act_fn(float z, float& d) {
+  if constexpr (ACT == SR_ACT_SOFTPLUS100) {
     const float bz = z * 100.0f;
-    if (bz > 20.0f) { d = 1.0f; return z; }
-    const float e = __expf(bz);
-    d = __fdividef(e, e + 1.0f);
-    return __logf(1.0f + e) * 0.01f;
+    const float e = __expf(fminf(bz, 20.0f));
+    const float sp = __logf(1.0f + e) * 0.01f;
+    const float dd = __fdividef(e, e + 1.0f);
+    d = bz > 20.0f ? 1.0f : dd;
+    return bz > 20.0f ? z : sp;
+  } else if constexpr (ACT == SR_ACT_RELU) {
+    d = z > 0.f ? 1.f : 0.f;
+    return fmaxf(z, 0.f);
+  } else if constexpr (ACT == SR_ACT_TANH) {
+    const float t = tanhf(z);
+    d = 1.f - t * t;
+    return t;
+  } else {
+    d = 1.f;
+    return z;
   }
-  if (act == SR_ACT_RELU) { d = z > 0.f ? 1.f : 0.f; return z > 0.f ? z : 0.f; }
-  if (act == SR_ACT_TANH) { const float t = tanhf(z); d = 1.f - t * t; return t; }
-  d = 1.f;
-  return z;
 }
 
+// two fp32 values -> three packed bf16 pairs (element 0 in the low half = lower address)
+__device__ __forceinline__ void split3x2(float x0, float x1, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+  p1 = *reinterpret_cast<uint32_t*>(&h);
+  const float r0 = x0 - __uint_as_float(p1 << 16), r1 = x1 - __uint_as_float(p1 & 0xffff0000u);
+  h = __floats2bfloat162_rn(r0, r1);
+  p2 = *reinterpret_cast<uint32_t*>(&h);
+  const float s0 = r0 - __uint_as_float(p2 << 16), s1 = r1 - __uint_as_float(p2 & 0xffff0000u);
+  h = __floats2bfloat162_rn(s0, s1);
+  p3 = *reinterpret_cast<uint32_t*>(&h);
+}
+
+struct EpiRow {
+  long long mt, row;
+  int nt, row_in_tile, lane;
+  bool row_ok, is_val;
+  size_t ds_ld;
+};
+
+// One 32-column chunk of the accumulator (this thread: one row): bias / activation / tangent
+// scaling (forward) or act' multiply (reverse), then the fp32 outputs, the act' stash and the
+// re-split bf16x3 tile of the next layer.  `live` = the chunk holds GEMM columns (else only the
+// zero padding / skip-connection columns of the next layer's input are produced).
+template <int ACT, int CH, bool MUL>
+__device__ __forceinline__ void epi_chunk(const LayerArgs& a, const EpiRow& r, uint32_t (&v)[32], int chunk,
+                                          bool live) {
+  const int c0 = r.nt * BN + chunk * 32;
+  float o[32];
+  if (live) {
+    if constexpr (MUL) {
+      // reverse sweep: delta * act'(z) for the columns that continue; columns >= n (the skip part of
+      // a skip layer's input gradient) pass through unscaled
+      if (c0 + 32 <= a.n) {
+        const float4* ms = reinterpret_cast<const float4*>(a.mul_src + (size_t)r.row * a.mul_ld + c0);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 m4 = r.row_ok ? __ldg(ms + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          o[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) * m4.x * a.scale;
+          o[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) * m4.y * a.scale;
+          o[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) * m4.z * a.scale;
+          o[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) * m4.w * a.scale;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float val = __uint_as_float(v[j]);
+          if (c0 + j < a.n) val = r.row_ok ? val * __ldg(a.mul_src + (size_t)r.row * a.mul_ld + c0 + j) : 0.f;
+          o[j] = val * a.scale;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + c0) + j4);
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = j4 * 4 + jj;
+          const float acc = __uint_as_float(v[j]);
+          float d = 1.f, val;
+          if constexpr (CH == 1) {
+            val = act_fn<ACT>(acc + bb[jj], d);
+          } else {
+            val = act_fn<ACT>(acc + bb[jj], d);                          // meaningful on value rows
+            const float dv = __shfl_sync(0xffffffffu, d, r.lane & ~3);  // act'(z) of the value row
+            if (!r.is_val) { val = dv * acc; }
+          }
+          o[j] = val * a.scale;
+          v[j] = __float_as_uint(d);
+        }
+      }
+      if (a.dstash != nullptr && r.is_val && r.row_ok) {
+        float4* dd = reinterpret_cast<float4*>(a.dstash + (size_t)r.row * r.ds_ld + c0);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4)
+          dd[j4] = make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]),
+                               __uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3]));
+      }
+    }
+    if (a.out != nullptr && r.row_ok && c0 < a.out_col0 + a.out_n && c0 + 32 > a.out_col0) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int c = c0 + j - a.out_col0;
+        if (c >= 0 && c < a.out_n) a.out[(size_t)r.row * a.out_ld + c] = o[j];
+      }
+    }
+  }
+  if (a.A_next == nullptr) return;
+  const int kcn = c0 >> 5;  // next layer's k chunk
+  if (kcn >= a.KCn) return;
+  if (!live || c0 + 32 > a.n) {  // zero padding / skip-connection columns (uniform branch)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int c = c0 + j;
+      if (!live || c >= a.n) {
+        float val = 0.f;
+        if (a.skip_src != nullptr && c >= a.n && c < a.n + a.skip_n && r.row_ok)
+          val = a.skip_src[(size_t)r.row * a.skip_ld + (c - a.n)] * a.scale;
+        o[j] = val;
+      }
+    }
+  }
+  __nv_bfloat16* base = a.A_next + a_tile_off(r.mt, kcn, a.KCn, 0) + (size_t)(r.row_in_tile >> 3) * 64 +
+                        (r.row_in_tile & 7) * 8;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint4 q1, q2, q3;
+    split3x2(o[g * 8 + 0], o[g * 8 + 1], q1.x, q2.x, q3.x);
+    split3x2(o[g * 8 + 2], o[g * 8 + 3], q1.y, q2.y, q3.y);
+    split3x2(o[g * 8 + 4], o[g * 8 + 5], q1.z, q2.z, q3.z);
+    split3x2(o[g * 8 + 6], o[g * 8 + 7], q1.w, q2.w, q3.w);
+    __nv_bfloat16* dst = base + (size_t)g * (BM * 8);
+    *reinterpret_cast<uint4*>(dst) = q1;
+    *reinterpret_cast<uint4*>(dst + A_PLANE) = q2;
+    *reinterpret_cast<uint4*>(dst + 2 * A_PLANE) = q3;
+  }
+}
+
+template <int ACT, int CH, bool MUL>
 __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(const __grid_constant__ LayerArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem);
@@ -181,9 +320,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(const __grid_cons
         const int nt = (int)(t % a.NT);
         for (int kc = 0; kc < a.KC; ++kc) {
           sr_mbar_wait(&empty[slot], phase ^ 1u);
+#ifdef SR_TC_DBG_NOLOAD   // tuning knock-out (tools/tc_diag.py): no operand traffic
+          sr_mbar_arrive(&full[slot]);
+#else
           sr_mbar_arrive_expect_tx(&full[slot], A_STAGE_BYTES + W_STAGE_BYTES);
           sr_bulk_g2s(sA + (size_t)slot * A_STAGE, a.A + a_tile_off(mt, kc, a.KC, 0), A_STAGE_BYTES, &full[slot]);
           sr_bulk_g2s(sW + (size_t)slot * W_STAGE, a.W + w_tile_off(nt, kc, a.KC, 0), W_STAGE_BYTES, &full[slot]);
+#endif
           if (++slot == STAGES) { slot = 0; phase ^= 1u; }
         }
       }
@@ -199,6 +342,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(const __grid_cons
       const int pa[6] = {0, 2, 1, 0, 1, 0};
       const int pw[6] = {2, 0, 1, 1, 0, 0};
       for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int nt = (int)(t % a.NT);
+        // N of this tile's MMAs: the GEMM's remaining columns rounded up to the instruction granule
+        int mma_n = a.n_gemm - nt * BN;
+        mma_n = mma_n >= BN ? BN : ((mma_n + 15) & ~15);
+        const uint32_t idesc = kIdescBase | ((uint32_t)(mma_n >> 3) << 17);
         sr_mbar_wait(&tempty[buf], bphase ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)buf * BN;
@@ -208,6 +356,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(const __grid_cons
           tc_fence_after();
           const uint32_t abase = sr_smem_u32(sA + (size_t)slot * A_STAGE);
           const uint32_t wbase = sr_smem_u32(sW + (size_t)slot * W_STAGE);
+#ifdef SR_TC_DBG_NOMMA    // tuning knock-out: 1/16 of the MMAs
+          if (kc == 0)
+#endif
 #pragma unroll
           for (int q = 0; q < 6; ++q) {
 #pragma unroll
@@ -215,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(const __grid_cons
               // K = 16 per MMA = two 8-wide core matrices: advance two LBO steps per j
               const uint64_t ad = make_desc(abase + pa[q] * (A_PLANE * 2) + j * 2 * (BM * 16), BM * 16, 128);
               const uint64_t bd = make_desc(wbase + pw[q] * (W_PLANE * 2) + j * 2 * (BN * 16), BN * 16, 128);
-              mma_bf16(tmem_d, ad, bd, accumulate);
+              mma_bf16(tmem_d, ad, bd, idesc, accumulate);
               accumulate = 1;
             }
           }
@@ -230,89 +381,46 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(const __grid_cons
     // ------------------------------------------------------------------ epilogue (warps 2..9)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;       // which half of the 256 accumulator columns
-    const int row_in_tile = q * 32 + lane;
-    const bool is_val = (a.ch == 1) || ((lane & 3) == 0);
-    const size_t ds_ld = (size_t)a.NT * BN;
+    EpiRow r;
+    r.row_in_tile = q * 32 + lane;
+    r.lane = lane;
+    r.is_val = (CH == 1) || ((lane & 3) == 0);
+    r.ds_ld = (size_t)a.NT * BN;
     int buf = 0;
     uint32_t bphase = 0;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      const long long mt = t / a.NT;
-      const int nt = (int)(t % a.NT);
-      const long long row = mt * BM + row_in_tile;
-      const bool row_ok = row < Mrows;
+      r.mt = t / a.NT;
+      r.nt = (int)(t % a.NT);
+      r.row = r.mt * BM + r.row_in_tile;
+      r.row_ok = r.row < Mrows;
+      const int c_base = r.nt * BN + half * 128;
+#ifdef SR_TC_DBG_NOEPI    // tuning knock-out: accumulators are drained without being read
+      const int n_live = 0;
+      if (t >= 0) r.row_ok = false;
+#else
+      const int n_live = (a.n_gemm - c_base + 31) >> 5;   // chunks of this warp's half that hold GEMM columns
+#endif
       sr_mbar_wait(&tfull[buf], bphase);
       tc_fence_after();
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * BN;
-      for (int chunk = half * 4; chunk < half * 4 + 4; ++chunk) {
-        uint32_t v[32];
-        tmem_ld32(taddr0 + chunk * 32, v);
-        const int c0 = nt * BN + chunk * 32;
-        float o[32];
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * BN + half * 128;
+      if constexpr (CH == 1 && !MUL) {
+        // two register buffers: the TMEM load of chunk i+1 is in flight while chunk i is processed
+        uint32_t va[32], vb[32];
+        if (n_live > 0) tmem_ld32_async(taddr0, va);
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + c0) + j4);
-          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int j = j4 * 4 + jj;
-            const float acc = __uint_as_float(v[j]);
-            float d = 1.f, val = 0.f;
-            if (a.mul_src != nullptr) {
-              // reverse sweep: delta * act'(z) for the columns that continue; columns >= n (the
-              // skip-connection part of a skip layer's input gradient) pass through unscaled by act'
-              val = acc;
-              if (c0 + j < a.n) val = row_ok ? acc * __ldg(a.mul_src + (size_t)row * a.mul_ld + c0 + j) : 0.f;
-            } else if (is_val) val = act_fn(a.act, acc + bb[jj], d);
-            if (a.ch == 4) {
-              const float dv = __shfl_sync(0xffffffffu, d, lane & ~3);  // act'(z) of the value row
-              if (!is_val) val = dv * acc;
-            }
-            o[j] = val * a.scale;
-            v[j] = __float_as_uint(d);
-          }
+        for (int i = 0; i < 4; i += 2) {
+          if (i < n_live) tmem_wait(va);
+          if (i + 1 < n_live) tmem_ld32_async(taddr0 + (i + 1) * 32, vb);
+          epi_chunk<ACT, CH, MUL>(a, r, va, half * 4 + i, i < n_live);
+          if (i + 1 < n_live) tmem_wait(vb);
+          if (i + 2 < 4 && i + 2 < n_live) tmem_ld32_async(taddr0 + (i + 2) * 32, va);
+          epi_chunk<ACT, CH, MUL>(a, r, vb, half * 4 + i + 1, i + 1 < n_live);
         }
-        if (a.dstash != nullptr && is_val && row_ok) {
-          float4* dd = reinterpret_cast<float4*>(a.dstash + (size_t)row * ds_ld + c0);
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4)
-            dd[j4] = make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]),
-                                 __uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3]));
-        }
-        if (a.out != nullptr && row_ok && c0 < a.out_col0 + a.out_n && c0 + 32 > a.out_col0) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = c0 + j - a.out_col0;
-            if (c >= 0 && c < a.out_n) a.out[(size_t)row * a.out_ld + c] = o[j];
-          }
-        }
-        if (c0 + 32 > a.n) {  // tail chunk: zero padding / skip-connection columns (uniform branch)
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = c0 + j;
-            if (c >= a.n) {
-              float val = 0.f;
-              if (a.skip_src != nullptr && c < a.n + a.skip_n && row_ok)
-                val = a.skip_src[(size_t)row * a.skip_ld + (c - a.n)] * a.scale;
-              o[j] = val;
-            }
-          }
-        }
-        if (a.A_next != nullptr) {
-          const int kcn = c0 >> 5;  // next layer's k chunk
-          if (kcn < a.KCn) {
-            __nv_bfloat16* base = a.A_next + a_tile_off(mt, kcn, a.KCn, 0) +
-                                  (size_t)(row_in_tile >> 3) * 64 + (row_in_tile & 7) * 8;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              __align__(16) __nv_bfloat16 p1[8], p2[8], p3[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) split3(o[g * 8 + e], p1[e], p2[e], p3[e]);
-              __nv_bfloat16* dst = base + (size_t)g * (BM * 8);
-              *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(p1);
-              *reinterpret_cast<uint4*>(dst + A_PLANE) = *reinterpret_cast<uint4*>(p2);
-              *reinterpret_cast<uint4*>(dst + 2 * A_PLANE) = *reinterpret_cast<uint4*>(p3);
-            }
-          }
+      } else {
+        for (int i = 0; i < 4; ++i) {
+          uint32_t v[32];
+          if (i < n_live) { tmem_ld32_async(taddr0 + i * 32, v); tmem_wait(v); }
+          epi_chunk<ACT, CH, MUL>(a, r, v, half * 4 + i, i < n_live);
         }
       }
       tc_fence_before();
@@ -498,20 +606,47 @@ int sr_tc_linear(const void* A, const void* W, const float* bias, int64_t M, int
   LayerArgs a;
   a.A = (const __nv_bfloat16*)A; a.W = (const __nv_bfloat16*)W; a.bias = bias; a.M = M;
   a.MT = (int)((M + BM - 1) / BM); a.NT = (N + BN - 1) / BN; a.KC = (K + 31) / 32;
-  a.n = n_valid; a.act = act; a.ch = ch;
+  a.n_gemm = N; a.n = n_valid; a.ch = ch;
   a.A_next = (__nv_bfloat16*)A_next; a.KCn = A_next ? (K_next + 31) / 32 : 0;
   a.scale = scale; a.skip_src = skip_src; a.skip_n = skip_n; a.skip_ld = skip_ld;
   a.out = out; a.out_ld = out_ld; a.dstash = dstash; a.out_col0 = out_col0; a.out_n = out_n;
   a.mul_src = mul_src; a.mul_ld = mul_ld; a.m_dev = m_dev;
+  if (mul_src && (mul_ld % 4 != 0 || ((uintptr_t)mul_src & 15))) return SR_EINVAL;
+  using Kern = void (*)(const LayerArgs);
+  Kern kern = nullptr;
+  if (mul_src) kern = tc_layer_kernel<SR_ACT_NONE, 1, true>;
+  else if (ch == 1) {
+    switch (act) {
+      case SR_ACT_NONE: kern = tc_layer_kernel<SR_ACT_NONE, 1, false>; break;
+      case SR_ACT_SOFTPLUS100: kern = tc_layer_kernel<SR_ACT_SOFTPLUS100, 1, false>; break;
+      case SR_ACT_RELU: kern = tc_layer_kernel<SR_ACT_RELU, 1, false>; break;
+      case SR_ACT_TANH: kern = tc_layer_kernel<SR_ACT_TANH, 1, false>; break;
+    }
+  } else {
+    switch (act) {
+      case SR_ACT_NONE: kern = tc_layer_kernel<SR_ACT_NONE, 4, false>; break;
+      case SR_ACT_SOFTPLUS100: kern = tc_layer_kernel<SR_ACT_SOFTPLUS100, 4, false>; break;
+      case SR_ACT_RELU: kern = tc_layer_kernel<SR_ACT_RELU, 4, false>; break;
+      case SR_ACT_TANH: kern = tc_layer_kernel<SR_ACT_TANH, 4, false>; break;
+    }
+  }
+  if (!kern) return SR_EINVAL;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
-    if (e != cudaSuccess) return (int)e;
+    Kern all[] = {tc_layer_kernel<SR_ACT_NONE, 1, true>,          tc_layer_kernel<SR_ACT_NONE, 1, false>,
+                  tc_layer_kernel<SR_ACT_SOFTPLUS100, 1, false>,  tc_layer_kernel<SR_ACT_RELU, 1, false>,
+                  tc_layer_kernel<SR_ACT_TANH, 1, false>,         tc_layer_kernel<SR_ACT_NONE, 4, false>,
+                  tc_layer_kernel<SR_ACT_SOFTPLUS100, 4, false>,  tc_layer_kernel<SR_ACT_RELU, 4, false>,
+                  tc_layer_kernel<SR_ACT_TANH, 4, false>};
+    for (Kern k : all) {
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+      if (e != cudaSuccess) return (int)e;
+    }
     attr_set = true;
   }
   const long long ntiles = (long long)a.MT * a.NT;
   const int grid = (int)(ntiles < SR_NUM_SMS_B200 ? ntiles : SR_NUM_SMS_B200);
-  tc_layer_kernel<<<grid, kThreads, kSmem, s>>>(a);
+  kern<<<grid, kThreads, kSmem, s>>>(a);
   return sr_launch_status();
 }
 }

@@ -90,7 +90,7 @@ class OptimNetwork(nn.Module):
         return verts, faces
 
     # ---- ray part of infer(): network.py:342-372 ------------------------------------------------
-    def infer_rays(self, batch_inds, row_inds, col_inds, initTmpPs, H, W, ratio, frame_ids, chunk=10000):
+    def infer_rays(self, batch_inds, row_inds, col_inds, initTmpPs, H, W, ratio, frame_ids, chunk=1 << 18):
         device = initTmpPs.device
         N = frame_ids.numel()
         cameras, _, _ = self._cameras(N, device)
@@ -105,12 +105,19 @@ class OptimNetwork(nn.Module):
             ps_, check = utils.OptimizeSurfacePs(cam_pos, rays_.detach(), ps_.clone(), bi_, self.sdf, ratio,
                                                  self.deformer, defconds, dthreshold=1.e-4, athreshold=self.angThred,
                                                  w1=3.05, w2=1., times=30)
-            _, nx, feat = self.sdf.forward_fused(ps_, ratio, want_grad=True, want_feat=True)
+            if hasattr(self.sdf, "forward_fused"):
+                tcolors.append(utils.shade_rays(self.sdf, self.deformer, self.netRender, ps_, rays_, defconds, bi_,
+                                                ratio)[2])
+                continue
+            ps_ = ps_.detach().requires_grad_(True)   # user-supplied field modules: reference sequence
+            sdfs = self.sdf(ps_, ratio)
+            nx = torch.autograd.grad(sdfs, ps_, torch.ones_like(sdfs))[0]
             nx = nx / nx.norm(dim=1, keepdim=True)
             crays, defVs = utils.compute_cardinal_rays(self.deformer, ps_, rays_, defconds, bi_, ratio, 'test')
             with torch.no_grad():
-                tcolors.append(utils.compute_netRender_color(self.netRender, ps_, defVs, nx, crays, feat,
-                                                             None, ratio))
+                self.sdf(ps_, ratio)
+                tcolors.append(utils.compute_netRender_color(self.netRender, ps_, defVs, nx, crays,
+                                                             self.sdf.rendcond, None, ratio))
         tcolors = torch.clamp((torch.cat(tcolors, dim=0) / 2. + 0.5) * 255., min=0., max=255.)
         colors = torch.ones(N, H, W, 3, device=device) * 255.
         colors[batch_inds, row_inds, col_inds, :] = tcolors

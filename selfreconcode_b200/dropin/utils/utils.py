@@ -133,3 +133,32 @@ def compute_cardinal_rays(deformer, ps, rays, defconds, batch_inds, ratio, phase
 
 def compute_netRender_color(net, ps, ds, ns, vs, features, framefeatures, ratio):
     return net(ps, ns, vs, features, ratio)
+
+
+def shade_rays(sdf, deformer, netRender, ps, rays, defconds, batch_inds, ratio):
+    """Everything the infer loop does with a traced point (model/network.py:356-368): template
+    normal grad f / |grad f|, cardinal ray J^-1 v, rendered colour.  -> (normals, crays, rgb), no
+    graph.  Large batches with the stock field modules run the SDF / translator sweeps (value +
+    3 forward tangents), the pointwise geometry and the rendering network back to back on the
+    tensor-core engine (ops.shade_and_render_tc); otherwise the per-op fused kernels are used."""
+    P = ps.shape[0]
+    stock = (_fusable(deformer) and hasattr(sdf, "fused") and hasattr(netRender, "fused")
+             and getattr(netRender, "mode", None) == 'idr' and getattr(netRender, "multires_n", 1) == 0
+             and getattr(sdf, "d_out", 0) == 1)
+    with torch.no_grad():
+        if stock and ops.TC_ENABLED and P >= ops.TC_MIN_POINTS:
+            tr, sk = deformer.defs[0], deformer.defs[1]
+            full = sdf.fused()
+            full.set_pe_weights(sdf._pe_weights(ratio['sdfRatio'] if isinstance(ratio, dict) else ratio))
+            poses, trans = defconds[1]
+            lbs = sk.lbs_state()
+            lbs.set_pose(poses.view(poses.shape[0], 24, 3), trans)
+            nfeat = full.desc.layer[full.desc.n_layers - 1].n - 1
+            n, cr, rgb, _, _ = ops.shade_and_render_tc(full, tr.fused(ratio), lbs, netRender.fused(ratio), ps, rays,
+                                                       batch_inds, defconds[0], nfeat=nfeat)
+            return n, cr, rgb
+        _, nx, feat = sdf.forward_fused(ps, ratio, want_grad=True, want_feat=True)
+        nx = nx / nx.norm(dim=1, keepdim=True)
+        crays, defVs = compute_cardinal_rays(deformer, ps, rays, defconds, batch_inds, ratio, 'test')
+        rgb = compute_netRender_color(netRender, ps, defVs, nx, crays, feat, None, ratio)
+    return nx, crays, rgb

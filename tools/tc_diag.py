@@ -1,0 +1,8 @@
+"""Builds debug variants of the tcgen05 layer kernel (loads / MMAs / epilogue knocked out one at
+a time) -- run here to build, run tools/tc_diag_run.sh on the GPU box."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from selfreconcode_b200 import build
+for tag, defs in [("noepi", ["SR_TC_DBG_NOEPI"]), ("nomma", ["SR_TC_DBG_NOMMA"]), ("noload", ["SR_TC_DBG_NOLOAD"])]:
+    print(tag, build.build_variant(tag, defs))
