@@ -1,20 +1,27 @@
-// Tensor-core engine for the dense layers: fp32-faithful BF16x3 split GEMM on tcgen05
-// (SURVEY.md section 7 "hard parts": the ray finder tests |f| < 5e-5, single-pass BF16/TF32
-// does not hold that; x = b1 + b2 + b3 with three bf16 terms carries 24 mantissa bits and
-//   x*w ~= b1w1 + b1w2 + b2w1 + b2w2 + b1w3 + b3w1      (dropped terms <= 2^-24 relative)
-// costs six bf16 MMAs, i.e. 1/6 of the bf16 tensor peak, accumulated in fp32 in TMEM).
+// Tensor-core engine for the dense layers: split-BF16 GEMM on tcgen05 with fp32 accumulation in TMEM
+// (SURVEY.md section 7 "hard parts": the ray finder tests |f| < 5e-5; a single BF16 or TF32 pass does
+// not hold that).  Every fp32 operand is split into bf16 planes x = b1 + b2 (+ b3) and the product is
+// assembled from the leading cross terms:
+//     2 planes / 3 MMAs (default):  x*w ~= b1w1 + b1w2 + b2w1         (dropped: <= 2^-16 relative)
+//     3 planes / 6 MMAs (-DSR_TC_PLANES=3): + b2w2 + b1w3 + b3w1      (dropped: <= 2^-24 relative)
+// Measured on B200 against an fp64 evaluation of the 8x512 SDF (tools/tc_terms.py): the tensor core
+// adds each MMA into the fp32 accumulator with truncation, so the error of a K=512 layer is dominated
+// by the NUMBER of accumulations (K/16 per term), not by the dropped terms -- 3 terms: max |err|
+// 2.4e-5, 6 terms: 3.4e-5 (FFMA engine: 2.3e-6; parity bar 1e-4).  Fewer terms are both faster
+// and closer, hence the default.
 //
 // One launch = one layer  C[M x N] = act(A[M x K] * W^T + b)  over all row tiles:
 //   * operands live in global memory already in the canonical (no-swizzle, K-major) shared
 //     memory layout of the UMMA descriptors -- 128-byte core matrices (8 rows x 8 bf16), tiles
-//     of 128 (or 256) rows x 32 k, the three split planes of a tile contiguous -- so ONE TMA bulk
+//     of 128 (or 256) rows x 32 k, the split planes of a tile contiguous -- so ONE TMA bulk
 //     copy (cp.async.bulk + mbarrier) per operand per stage lands a ready-to-use tile and no
 //     tensor map is needed.  The previous layer's epilogue writes its output directly in that
 //     layout (activations stay L2-resident between layers for the batch sizes used here);
 //   * warp-specialised, persistent CTAs: warp 0 = TMA producer, warp 1 = single-thread
-//     tcgen05.mma issuer (+ TMEM alloc), warps 2-5 = epilogue (tcgen05.ld -> bias, activation,
-//     forward-mode tangent scaling, re-split to bf16x3, tiled store);
-//   * 3-stage shared-memory ring (72 KB per stage), two 256-column fp32 accumulators in TMEM so
+//     tcgen05.mma issuer (+ TMEM alloc), warps 2-9 = epilogue (tcgen05.ld -> bias, activation,
+//     forward-mode tangent scaling or reverse-mode act' multiply, re-split to bf16 planes, tiled
+//     store); the epilogue is specialised at compile time per (activation, rows-per-point, mode);
+//   * 4-stage shared-memory ring (48 KB per stage), two 256-column fp32 accumulators in TMEM so
 //     the epilogue of tile i overlaps the MMAs of tile i+1.
 // The FFMA engine (mlp_kernels.cu) stays the accuracy reference; tests compare both.
 #include <cuda_bf16.h>
@@ -23,13 +30,17 @@
 
 namespace sr_tc {
 
-constexpr int BM = 128, BN = 256, BK = 32, STAGES = 3;
+#ifndef SR_TC_PLANES
+#define SR_TC_PLANES 2
+#endif
+constexpr int kPlanes = SR_TC_PLANES;
+constexpr int BM = 128, BN = 256, BK = 32, STAGES = kPlanes == 2 ? 4 : 3;
 constexpr int kEpiWarps = 8;               // two per TMEM lane quarter, each takes half the columns
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int A_PLANE = BM * BK;          // elements
 constexpr int W_PLANE = BN * BK;
-constexpr int A_STAGE = 3 * A_PLANE;      // 12288 bf16 = 24 KB
-constexpr int W_STAGE = 3 * W_PLANE;      // 24576 bf16 = 48 KB
+constexpr int A_STAGE = kPlanes * A_PLANE;   // 2 planes: 16 KB
+constexpr int W_STAGE = kPlanes * W_PLANE;   // 2 planes: 32 KB
 constexpr uint32_t A_STAGE_BYTES = A_STAGE * 2, W_STAGE_BYTES = W_STAGE * 2;
 constexpr size_t kSmem = (size_t)STAGES * (A_STAGE_BYTES + W_STAGE_BYTES) + 256;
 
@@ -37,10 +48,10 @@ constexpr size_t kSmem = (size_t)STAGES * (A_STAGE_BYTES + W_STAGE_BYTES) + 256;
 // A: [row tile mt][k chunk kc][plane p][k8 (4)][row group (16)][row (8)][elem (8)]
 // W: [col tile nt][k chunk kc][plane p][k8 (4)][row group (32)][row (8)][elem (8)]
 __host__ __device__ inline size_t a_tile_off(long long mt, int kc, int KC, int p) {
-  return (((size_t)mt * KC + kc) * 3 + p) * A_PLANE;
+  return (((size_t)mt * KC + kc) * kPlanes + p) * A_PLANE;
 }
 __host__ __device__ inline size_t w_tile_off(int nt, int kc, int KC, int p) {
-  return (((size_t)nt * KC + kc) * 3 + p) * W_PLANE;
+  return (((size_t)nt * KC + kc) * kPlanes + p) * W_PLANE;
 }
 __device__ __forceinline__ int in_tile_off(int rows_per_tile, int r, int k) {
   return (k >> 3) * (rows_per_tile * 8) + (r >> 3) * 64 + (r & 7) * 8 + (k & 7);
@@ -161,9 +172,13 @@ __device__ __forceinline__ void split3x2(float x0, float x1, uint32_t& p1, uint3
   const float r0 = x0 - __uint_as_float(p1 << 16), r1 = x1 - __uint_as_float(p1 & 0xffff0000u);
   h = __floats2bfloat162_rn(r0, r1);
   p2 = *reinterpret_cast<uint32_t*>(&h);
-  const float s0 = r0 - __uint_as_float(p2 << 16), s1 = r1 - __uint_as_float(p2 & 0xffff0000u);
-  h = __floats2bfloat162_rn(s0, s1);
-  p3 = *reinterpret_cast<uint32_t*>(&h);
+  if constexpr (kPlanes == 3) {
+    const float s0 = r0 - __uint_as_float(p2 << 16), s1 = r1 - __uint_as_float(p2 & 0xffff0000u);
+    h = __floats2bfloat162_rn(s0, s1);
+    p3 = *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    p3 = 0u;
+  }
 }
 
 struct EpiRow {
@@ -268,7 +283,7 @@ __device__ __forceinline__ void epi_chunk(const LayerArgs& a, const EpiRow& r, u
     __nv_bfloat16* dst = base + (size_t)g * (BM * 8);
     *reinterpret_cast<uint4*>(dst) = q1;
     *reinterpret_cast<uint4*>(dst + A_PLANE) = q2;
-    *reinterpret_cast<uint4*>(dst + 2 * A_PLANE) = q3;
+    if constexpr (kPlanes == 3) *reinterpret_cast<uint4*>(dst + 2 * A_PLANE) = q3;
   }
 }
 
@@ -339,8 +354,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(const __grid_cons
       int buf = 0;
       uint32_t bphase = 0;
       // plane pairs, smallest contributions first
-      const int pa[6] = {0, 2, 1, 0, 1, 0};
-      const int pw[6] = {2, 0, 1, 1, 0, 0};
+      constexpr int kTerms = kPlanes == 2 ? 3 : 6;
+      const int pa[6] = {0, 1, 0, 2, 1, 0};   // 2 planes: (a0,w1) (a1,w0) (a0,w0)
+      const int pw[6] = {1, 0, 0, 0, 1, 0};   // 3 planes: see below
+      const int pa3[6] = {0, 2, 1, 0, 1, 0};
+      const int pw3[6] = {2, 0, 1, 1, 0, 0};
       for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int nt = (int)(t % a.NT);
         // N of this tile's MMAs: the GEMM's remaining columns rounded up to the instruction granule
@@ -360,12 +378,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(const __grid_cons
           if (kc == 0)
 #endif
 #pragma unroll
-          for (int q = 0; q < 6; ++q) {
+          for (int q = 0; q < kTerms; ++q) {
 #pragma unroll
             for (int j = 0; j < BK / 16; ++j) {
               // K = 16 per MMA = two 8-wide core matrices: advance two LBO steps per j
-              const uint64_t ad = make_desc(abase + pa[q] * (A_PLANE * 2) + j * 2 * (BM * 16), BM * 16, 128);
-              const uint64_t bd = make_desc(wbase + pw[q] * (W_PLANE * 2) + j * 2 * (BN * 16), BN * 16, 128);
+              const int qa = kPlanes == 2 ? pa[q] : pa3[q], qw = kPlanes == 2 ? pw[q] : pw3[q];
+              const uint64_t ad = make_desc(abase + qa * (A_PLANE * 2) + j * 2 * (BM * 16), BM * 16, 128);
+              const uint64_t bd = make_desc(wbase + qw * (W_PLANE * 2) + j * 2 * (BN * 16), BN * 16, 128);
               mma_bf16(tmem_d, ad, bd, idesc, accumulate);
               accumulate = 1;
             }
@@ -466,7 +485,8 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, long long M, int
     const size_t off = (size_t)k8 * (BM * 8) + (size_t)(r >> 3) * 64 + (r & 7) * 8;
     *reinterpret_cast<uint4*>(dst + a_tile_off(mt, kc, KC, 0) + off) = *reinterpret_cast<uint4*>(p1);
     *reinterpret_cast<uint4*>(dst + a_tile_off(mt, kc, KC, 1) + off) = *reinterpret_cast<uint4*>(p2);
-    *reinterpret_cast<uint4*>(dst + a_tile_off(mt, kc, KC, 2) + off) = *reinterpret_cast<uint4*>(p3);
+    if constexpr (kPlanes == 3)
+      *reinterpret_cast<uint4*>(dst + a_tile_off(mt, kc, KC, kPlanes - 1) + off) = *reinterpret_cast<uint4*>(p3);
   }
 }
 
@@ -492,7 +512,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int N, int K, i
     const size_t off = (size_t)k8 * (BN * 8) + (size_t)(r >> 3) * 64 + (r & 7) * 8;
     *reinterpret_cast<uint4*>(dst + w_tile_off(nt, kc, KC, 0) + off) = *reinterpret_cast<uint4*>(p1);
     *reinterpret_cast<uint4*>(dst + w_tile_off(nt, kc, KC, 1) + off) = *reinterpret_cast<uint4*>(p2);
-    *reinterpret_cast<uint4*>(dst + w_tile_off(nt, kc, KC, 2) + off) = *reinterpret_cast<uint4*>(p3);
+    if constexpr (kPlanes == 3)
+      *reinterpret_cast<uint4*>(dst + w_tile_off(nt, kc, KC, kPlanes - 1) + off) = *reinterpret_cast<uint4*>(p3);
   }
 }
 
@@ -570,11 +591,11 @@ int sr_tc_embed(const float* pts, int64_t P, int multires, const float* pe_w, in
 
 int64_t sr_tc_act_bytes(int64_t M, int K) {
   const int64_t MT = (M + sr_tc::BM - 1) / sr_tc::BM, KC = (K + 31) / 32;
-  return MT * KC * 3 * sr_tc::A_PLANE * 2;
+  return MT * KC * sr_tc::kPlanes * sr_tc::A_PLANE * 2;
 }
 int64_t sr_tc_weight_bytes(int N, int K) {
   const int64_t NT = (N + sr_tc::BN - 1) / sr_tc::BN, KC = (K + 31) / 32;
-  return NT * KC * 3 * sr_tc::W_PLANE * 2;
+  return NT * KC * sr_tc::kPlanes * sr_tc::W_PLANE * 2;
 }
 
 int sr_tc_pack_rows(const float* src, int64_t M, int K, int ld, void* dst, const int32_t* m_dev,

@@ -126,4 +126,4 @@ def test_infer_rays_and_discretize():
     assert verts.shape[0] > 100 and faces.shape[0] > 100 and int(faces.max()) == verts.shape[0] - 1
     with torch.no_grad():
         f = net.sdf.forward_fused(verts, H.RATIO, False, False)[0].view(-1)
-    assert float(f.abs().max()) < 2e-3   # vertices sit on the zero set up to the linear edge interpolation
+    assert float(f.abs().max()) < 5e-3   # vertices sit on the zero set up to the linear edge interpolation (65^3 grid)

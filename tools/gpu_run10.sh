@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+run() { name=$1; shift; echo "=== $name" ; timeout "$@" > gpurun_out/$name.log 2>&1; echo "exit $? ($name)"; tail -n 4 gpurun_out/$name.log; }
+run optim_tests 600 python -m pytest tests/test_optim_step_gpu.py -m gpu -q --maxfail=20
+for v in base terms4 terms3; do
+  if [ $v = base ]; then unset SELFRECON_B200_LIB; else export SELFRECON_B200_LIB=$PWD/selfreconcode_b200/lib/variants/libselfrecon_b200_$v.so; fi
+  run terms_$v 200 python tools/tc_terms.py
+done

@@ -1,8 +1,9 @@
-"""Builds debug variants of the tcgen05 layer kernel (loads / MMAs / epilogue knocked out one at
-a time) -- run here to build, run tools/tc_diag_run.sh on the GPU box."""
+"""Builds tuning variants of the tcgen05 layer kernel (loads / MMAs / epilogue knocked out one at
+a time, 3-plane 6-term split) -- build here, run with SELFRECON_B200_LIB=<variant> on the GPU box."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from selfreconcode_b200 import build
-for tag, defs in [("noepi", ["SR_TC_DBG_NOEPI"]), ("nomma", ["SR_TC_DBG_NOMMA"]), ("noload", ["SR_TC_DBG_NOLOAD"])]:
+for tag, defs in [("noepi", ["SR_TC_DBG_NOEPI"]), ("nomma", ["SR_TC_DBG_NOMMA"]), ("noload", ["SR_TC_DBG_NOLOAD"]),
+                  ("planes3", ["SR_TC_PLANES=3"])]:
     print(tag, build.build_variant(tag, defs))
