@@ -230,23 +230,35 @@ def cpu_reference_sample(n_rays, threads, seed=0, with_mc=True):
         t0 = time.perf_counter()
         with torch.no_grad():
             grid, calc = O.seg3d_forward(lambda q: sdf_fn(q).view(-1), [-1.0] * 3, [1.0] * 3,
-                                         synth.MC_LADDER_65, 0.0)
-        spc, org = O.mc_world_params([-1.0] * 3, [1.0] * 3, (65, 65, 65))
+                                         synth.MC_LADDER_129, 0.0)
+        spc, org = O.mc_world_params([-1.0] * 3, [1.0] * 3, (129, 129, 129))
         c_api.marching_cubes(grid.permute(2, 1, 0).contiguous().numpy(), helpers.mc_tri_table(), 0.0, spc, org)
         t_mc = time.perf_counter() - t0
-        out.update({"mc_grid": 65, "mc_seconds": t_mc, "mc_voxels_per_sec": 65 ** 3 / t_mc,
+        out.update({"mc_grid": 129, "mc_seconds": t_mc, "mc_voxels_per_sec": 129 ** 3 / t_mc,
                     "mc_queried": int(calc.sum())})
     return out
+
+
+def pick_threads():
+    """Thread count at which the CPU port is fastest on this host (the matrices are small: beyond a
+    few dozen threads torch's intra-op pool only adds contention -- measured 128 -> 32 threads: 10x)."""
+    ncpu = os.cpu_count() or 1
+    best, best_v = 1, 0.0
+    for t in sorted({min(t, ncpu) for t in (8, 16, 32, 64, ncpu)}):
+        v = cpu_reference_sample(1024, t, with_mc=False)["rays_per_sec"]
+        if v > best_v:
+            best, best_v = t, v
+    return best
 
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path (oracle port) on host cores, bounded sample."""
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    n = 192
+    threads = pick_threads()
+    n = 8192
     for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_reference_sample(32, threads, with_mc=False)
+        cpu_reference_sample(512, threads, with_mc=False)
     vals, ts = [], []
     for _ in range(args.steps):
         r = cpu_reference_sample(n, threads, with_mc=False)
@@ -439,10 +451,10 @@ def main():
         "wall_s_timed_region": t_wall,
     }
     if not args.no_cpu_baseline and world == 1:
-        threads = min(os.cpu_count() or 1, 32)   # small matrices: more threads only add contention
-        cb = cpu_reference_sample(96, threads, with_mc=True)
+        threads = pick_threads()
+        cb = cpu_reference_sample(16384, threads, with_mc=True)
         line["cpu_baseline"] = {"value": cb["rays_per_sec"], "unit": "rays/s", "cores": threads, "kind": "port",
-                                "sample": "96 rays of the same frame (trace times=10 + shading) and a 65^3 "
+                                "sample": "16384 rays of the same frame (trace times=10 + shading) and a 129^3 "
                                           "coarse-to-fine grid + MC through oracle/ (torch fp32 CPU + C)",
                                 "mc_voxels_per_sec": cb.get("mc_voxels_per_sec"), "mc_grid": cb.get("mc_grid"),
                                 "ray_seconds": cb["ray_seconds"], "mc_seconds": cb.get("mc_seconds")}

@@ -205,6 +205,7 @@ def ang_threshold(cam, pixoffset=0.5):
 MC_LADDER_257 = [(33, 33, 33), (65, 65, 65), (129, 129, 129), (257, 257, 257)]
 MC_LADDER_513 = MC_LADDER_257 + [(513, 513, 513)]
 MC_LADDER_65 = [(9, 9, 9), (17, 17, 17), (33, 33, 33), (65, 65, 65)]
+MC_LADDER_129 = [(17, 17, 17), (33, 33, 33), (65, 65, 65), (129, 129, 129)]
 
 
 class Conf(dict):
