@@ -269,10 +269,13 @@ int sr_shade_geometry(const sr_mlp_desc* sdf, const sr_mlp_desc* dnet, const sr_
  *                        columns [n_valid, n_valid+skip_n) taken from skip_src (the skip concat of
  *                        network.py:88-89) and the rest zero; out (fp32 [M][out_ld], may be NULL)
  *                        receives result columns [out_col0, out_col0+out_n); dstash (fp32
- *                        [M][pad256(N)], may be NULL) receives act'(z) of value rows; mul_src
- *                        (fp32 [M][mul_ld], may be NULL) switches the epilogue to
- *                        out = acc * mul_src (the reverse-mode sweep: delta * act'); m_dev
- *                        (may be NULL) is a device-side row count <= M (active rays).
+ *                        [M][pad256(N)], may be NULL) receives act'(z) of value rows; mul_tiles
+ *                        (may be NULL) switches the epilogue to the reverse-mode sweep
+ *                        out = acc * act'(z_prev): act' is recomputed from the previous layer's
+ *                        stored output a = mul_tiles (tiled, mul_K columns, stored as mul_scale*a by
+ *                        the forward pass) -- softplus100: 1-exp(-100a), relu: a>0 (mul_act) -- so
+ *                        the forward sweep writes no separate stash; m_dev (may be NULL) is a
+ *                        device-side row count <= M (active rays).
  * Replaces the nn.Linear / cuBLAS calls of ImplicitNetwork / MLPTranslator / RenderNet for
  * large batches (model/network.py:85-94, Deformer.py:64-69, RenderNet.py:80-88).
  * ------------------------------------------------------------------------------------------ */
@@ -290,12 +293,12 @@ int sr_tc_pack_weights(const float* w, int N, int K, int ld, void* dst, cudaStre
 int sr_tc_linear(const void* A, const void* W, const float* bias, int64_t M, int N, int K,
                  int n_valid, int act, int ch, void* A_next, int K_next, float scale,
                  const float* skip_src, int skip_n, int skip_ld, float* out, int out_ld,
-                 int out_col0, int out_n, float* dstash, const float* mul_src, int mul_ld,
-                 const int32_t* m_dev, cudaStream_t s);
+                 int out_col0, int out_n, float* dstash, const void* mul_tiles, int mul_K, int mul_act,
+                 float mul_scale, const int32_t* m_dev, cudaStream_t s);
 
 /* Pointwise stages of the tensor-core tracer (one OptimizeSurfacePs iteration =
- * embed -> sr_tc_linear x layers (forward, act' stashed) -> sr_tc_trace_mid -> sr_tc_linear x
- * layers (reverse sweep, mul_src = stash) -> sr_tc_trace_update).  All take an optional active
+ * embed -> sr_tc_linear x layers (forward, activations kept per layer) -> sr_tc_trace_mid -> sr_tc_linear x
+ * layers (reverse sweep, mul_tiles = the forward activations) -> sr_tc_trace_update).  All take an optional active
  * list + device-side count so the host never synchronises.  pw_s / pw_d are HOST arrays. */
 int sr_tc_trace_mid(const int32_t* index, const int32_t* m_dev, int64_t P, const float* pts,
                     const float* rays, const int64_t* batch_inds, const float* f, const float* off,

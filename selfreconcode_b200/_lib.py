@@ -98,7 +98,7 @@ SIGNATURES = {
     "sr_tc_pack_rows": (C.c_int, [c_f, i64, i32, i32, c_f, c_f, stream_t]),
     "sr_tc_pack_weights": (C.c_int, [c_f, i32, i32, i32, c_f, stream_t]),
     "sr_tc_linear": (C.c_int, [c_f, c_f, c_f, i64, i32, i32, i32, i32, i32, c_f, i32, f32, c_f, i32,
-                               i32, c_f, i32, i32, i32, c_f, c_f, i32, c_f, stream_t]),
+                               i32, c_f, i32, i32, i32, c_f, c_f, i32, i32, f32, c_f, stream_t]),
     "sr_tc_trace_mid": (C.c_int, [c_f, c_f, i64, c_f, c_f, c_f, c_f, c_f, C.POINTER(LbsParams),
                                   C.POINTER(TraceParams), i32, c_f, c_f, c_f, i32, c_f, stream_t]),
     "sr_tc_trace_update": (C.c_int, [c_f, c_f, i64, c_f, c_f, i32, c_f, i32, c_f, i32, c_f, i32,

@@ -136,8 +136,12 @@ struct LayerArgs {
   float* out;               // fp32 row-major [M][out_ld] (last layer), columns [0, n)
   int out_ld;
   float* dstash;            // fp32 row-major [M][NT*256] act'(z) of value rows (reverse mode) or null
-  const float* mul_src;     // fp32 [M][mul_ld] or null: out = acc * mul_src (backward sweep: act' stash)
-  int mul_ld;
+  // reverse sweep (MUL kernels): out = acc * act'(z_prev), act' recomputed from the previous layer's
+  // stored output a (the tiles the forward pass wrote for this layer's input, scaled by 1/mul_inv_scale):
+  // softplus100: 1 - exp(-100 a), relu: a > 0
+  const __nv_bfloat16* mul_tiles;
+  int mul_KC;
+  float mul_inv_scale;
   int out_col0;             // `out` receives columns [out_col0, out_col0 + out_n) of the result
   int out_n;
   const int* m_dev;         // optional device-side row count (active rays); M is the upper bound
@@ -200,22 +204,27 @@ __device__ __forceinline__ void epi_chunk(const LayerArgs& a, const EpiRow& r, u
   if (live) {
     if constexpr (MUL) {
       // reverse sweep: delta * act'(z) for the columns that continue; columns >= n (the skip part of
-      // a skip layer's input gradient) pass through unscaled
-      if (c0 + 32 <= a.n) {
-        const float4* ms = reinterpret_cast<const float4*>(a.mul_src + (size_t)r.row * a.mul_ld + c0);
+      // a skip layer's input gradient) pass through unscaled.  ACT is the PREVIOUS layer's activation.
+      const __nv_bfloat16* mt = a.mul_tiles + a_tile_off(r.mt, c0 >> 5, a.mul_KC, 0) +
+                                (size_t)(r.row_in_tile >> 3) * 64 + (r.row_in_tile & 7) * 8;
+      const float kk = -100.0f * a.mul_inv_scale;
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 m4 = r.row_ok ? __ldg(ms + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          o[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) * m4.x * a.scale;
-          o[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) * m4.y * a.scale;
-          o[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) * m4.z * a.scale;
-          o[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) * m4.w * a.scale;
-        }
-      } else {
+      for (int g = 0; g < 4; ++g) {
+        const uint4 q0 = *reinterpret_cast<const uint4*>(mt + (size_t)g * (BM * 8));
+        const uint4 q1 = *reinterpret_cast<const uint4*>(mt + (size_t)g * (BM * 8) + A_PLANE);
+        const uint32_t w0[4] = {q0.x, q0.y, q0.z, q0.w}, w1[4] = {q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int e = 0; e < 8; ++e) {
+          const int j = g * 8 + e;
+          const uint32_t h0 = w0[e >> 1], h1 = w1[e >> 1];
+          const float as = (e & 1) ? __uint_as_float(h0 & 0xffff0000u) + __uint_as_float(h1 & 0xffff0000u)
+                                   : __uint_as_float(h0 << 16) + __uint_as_float(h1 << 16);
+          float d;
+          if constexpr (ACT == SR_ACT_SOFTPLUS100) d = 1.0f - __expf(kk * as);
+          else if constexpr (ACT == SR_ACT_RELU) d = as > 0.f ? 1.f : 0.f;
+          else d = 1.f;
           float val = __uint_as_float(v[j]);
-          if (c0 + j < a.n) val = r.row_ok ? val * __ldg(a.mul_src + (size_t)r.row * a.mul_ld + c0 + j) : 0.f;
+          if (c0 + j < a.n) val = r.row_ok ? val * d : 0.f;
           o[j] = val * a.scale;
         }
       }
@@ -619,8 +628,8 @@ int sr_tc_pack_weights(const float* w, int N, int K, int ld, void* dst, cudaStre
 int sr_tc_linear(const void* A, const void* W, const float* bias, int64_t M, int N, int K, int n_valid,
                  int act, int ch, void* A_next, int K_next, float scale, const float* skip_src,
                  int skip_n, int skip_ld, float* out, int out_ld, int out_col0, int out_n,
-                 float* dstash, const float* mul_src, int mul_ld, const int32_t* m_dev,
-                 cudaStream_t s) {
+                 float* dstash, const void* mul_tiles, int mul_K, int mul_act, float mul_scale,
+                 const int32_t* m_dev, cudaStream_t s) {
   using namespace sr_tc;
   if (!A || !W || !bias || M <= 0 || N <= 0 || K <= 0 || (ch != 1 && ch != 4)) return SR_EINVAL;
   if (!A_next && !out) return SR_EINVAL;
@@ -631,12 +640,18 @@ int sr_tc_linear(const void* A, const void* W, const float* bias, int64_t M, int
   a.A_next = (__nv_bfloat16*)A_next; a.KCn = A_next ? (K_next + 31) / 32 : 0;
   a.scale = scale; a.skip_src = skip_src; a.skip_n = skip_n; a.skip_ld = skip_ld;
   a.out = out; a.out_ld = out_ld; a.dstash = dstash; a.out_col0 = out_col0; a.out_n = out_n;
-  a.mul_src = mul_src; a.mul_ld = mul_ld; a.m_dev = m_dev;
-  if (mul_src && (mul_ld % 4 != 0 || ((uintptr_t)mul_src & 15))) return SR_EINVAL;
+  a.mul_tiles = (const __nv_bfloat16*)mul_tiles; a.mul_KC = (mul_K + 31) / 32;
+  a.mul_inv_scale = mul_scale != 0.f ? 1.0f / mul_scale : 1.0f; a.m_dev = m_dev;
+  if (mul_tiles && (ch != 1 || mul_K < n_valid)) return SR_EINVAL;
   using Kern = void (*)(const LayerArgs);
   Kern kern = nullptr;
-  if (mul_src) kern = tc_layer_kernel<SR_ACT_NONE, 1, true>;
-  else if (ch == 1) {
+  if (mul_tiles) {
+    switch (mul_act) {
+      case SR_ACT_NONE: kern = tc_layer_kernel<SR_ACT_NONE, 1, true>; break;
+      case SR_ACT_SOFTPLUS100: kern = tc_layer_kernel<SR_ACT_SOFTPLUS100, 1, true>; break;
+      case SR_ACT_RELU: kern = tc_layer_kernel<SR_ACT_RELU, 1, true>; break;
+    }
+  } else if (ch == 1) {
     switch (act) {
       case SR_ACT_NONE: kern = tc_layer_kernel<SR_ACT_NONE, 1, false>; break;
       case SR_ACT_SOFTPLUS100: kern = tc_layer_kernel<SR_ACT_SOFTPLUS100, 1, false>; break;
@@ -654,7 +669,8 @@ int sr_tc_linear(const void* A, const void* W, const float* bias, int64_t M, int
   if (!kern) return SR_EINVAL;
   static bool attr_set = false;
   if (!attr_set) {
-    Kern all[] = {tc_layer_kernel<SR_ACT_NONE, 1, true>,          tc_layer_kernel<SR_ACT_NONE, 1, false>,
+    Kern all[] = {tc_layer_kernel<SR_ACT_NONE, 1, true>,          tc_layer_kernel<SR_ACT_SOFTPLUS100, 1, true>,
+                  tc_layer_kernel<SR_ACT_RELU, 1, true>,          tc_layer_kernel<SR_ACT_NONE, 1, false>,
                   tc_layer_kernel<SR_ACT_SOFTPLUS100, 1, false>,  tc_layer_kernel<SR_ACT_RELU, 1, false>,
                   tc_layer_kernel<SR_ACT_TANH, 1, false>,         tc_layer_kernel<SR_ACT_NONE, 4, false>,
                   tc_layer_kernel<SR_ACT_SOFTPLUS100, 4, false>,  tc_layer_kernel<SR_ACT_RELU, 4, false>,

@@ -22,6 +22,8 @@ import os as _os
 TC_ENABLED = _os.environ.get("SELFRECON_B200_TC", "1") != "0"
 TC_MIN_POINTS = int(_os.environ.get("SELFRECON_B200_TC_MIN_POINTS", "16384"))
 
+import itertools as _it
+_uid_counter = _it.count()
 LAUNCHES = 0  # kernels launched by this module since it was last reset (bench.py reads it)
 
 _KERNELS_PER_CALL = {"mc_count": 2}
@@ -247,6 +249,7 @@ class FusedMLP:
         self.bufs = []
         self.desc = MlpDesc()
         self._sig = None
+        self.uid = next(_uid_counter)   # identity for caches (id() can be recycled)
 
     def fold(self, linears, pe_w=None):
         lib = _lib.load()
@@ -580,7 +583,7 @@ def tc_linear(A, W, bias, M, N, K, n_valid, act, ch=1, K_next=0, scale=1.0, skip
         check(lib.sr_tc_linear(_p(A), _p(W), _p(b), M, N, K, n_valid, int(act), int(ch), _p(A_next),
                                int(K_next), float(scale), _p(skip_src), int(skip_n),
                                skip_src.shape[1] if skip_src is not None else 0, _p(out),
-                               n_valid if want_out else 0, 0, n_valid, _p(ds), None, 0, None, _stream()),
+                               n_valid if want_out else 0, 0, n_valid, _p(ds), None, 0, 0, 1.0, None, _stream()),
               "tc_linear")
     return A_next, out, ds
 
@@ -667,7 +670,7 @@ def tc_mlp_forward(fused, pts, ch=1, conds=None, batch_inds=None, pts_per_frame=
             check(lib.sr_tc_linear(_p(A), _p(ly["W"]), _p(ly["bias"]), M, ly["n"], K, nv, ly["act"], ch,
                                    _p(A_next), Kn, 0.7071067811865476 if skip_next else 1.0,
                                    _p(emb) if skip_next else None, d.d_in if skip_next else 0, ld, _p(o),
-                                   nv if last else 0, 0, nv, _p(ds), None, 0, None, _stream()), "tc_linear")
+                                   nv if last else 0, 0, nv, _p(ds), None, 0, 0, 1.0, None, _stream()), "tc_linear")
             if ds is not None:
                 stashes.append(ds)
             A, K, out = A_next, Kn, o
@@ -686,7 +689,9 @@ class _TcTraceBuffers:
         self.emb_s = f32(P, self.ld_s)
         self.A = [u8(lib.sr_tc_act_bytes(P, 512)) for _ in range(2)]
         self.f = f32(P, 1)
-        self.ds_s = [f32(P, _pad(sdf_net.desc.layer[i].n, 256)) for i in range(sdf_net.desc.n_layers - 1)]
+        self.A_in = u8(lib.sr_tc_act_bytes(P, 256))
+        self.acts_s = [u8(lib.sr_tc_act_bytes(P, _pad(sdf_net.desc.layer[i + 1].k, 32)))
+                       for i in range(sdf_net.desc.n_layers - 1)]
         self.cot_s = f32(P, 32)
         self.cot_d = f32(P, 32)
         self.aux = f32(P, 8)
@@ -696,37 +701,39 @@ class _TcTraceBuffers:
             self.ld_d = _pad(def_net.desc.d_in, 32)
             self.emb_d = f32(P, self.ld_d)
             self.off = f32(P, 3)
-            self.ds_d = [f32(P, _pad(def_net.desc.layer[i].n, 256)) for i in range(def_net.desc.n_layers - 1)]
+            self.acts_d = [u8(lib.sr_tc_act_bytes(P, _pad(def_net.desc.layer[i + 1].k, 32)))
+                           for i in range(def_net.desc.n_layers - 1)]
             self.gd = f32(P, 64)
 
 
-_tc_trace_bufs = {}
 
 
-def _tc_forward_sweep(lib, net, tcn, emb, ld, A_bufs, P, m_dev, out, stashes):
-    """embedded input (already in `emb`) -> all layers; last layer -> `out` fp32 [P][n_last]."""
+def _tc_forward_sweep(lib, net, tcn, emb, ld, A_in, acts, P, m_dev, out):
+    """embedded input (already in `emb`) -> all layers; layer i writes its output tiles to acts[i]
+    (kept for the reverse sweep, which recomputes act' from them); last layer -> `out` fp32."""
     d = net.desc
-    check(lib.sr_tc_pack_rows(_p(emb), P, ld, ld, _p(A_bufs[0]), _p(m_dev), _stream()), "tc_pack_rows")
+    check(lib.sr_tc_pack_rows(_p(emb), P, ld, ld, _p(A_in), _p(m_dev), _stream()), "tc_pack_rows")
     K = ld
-    cur = 0
+    cur = A_in
     L = len(tcn.layers)
     for i, ly in enumerate(tcn.layers):
         last = i == L - 1
         nxt = tcn.layers[i + 1] if not last else None
         Kn = _pad(nxt["k"], 32) if nxt else 0
         skip_next = bool(nxt and nxt["skip"])
-        check(lib.sr_tc_linear(_p(A_bufs[cur]), _p(ly["W"]), _p(ly["bias"]), P, ly["n"], K, ly["n"], ly["act"], 1,
-                               _p(A_bufs[1 - cur]) if nxt else None, Kn,
+        check(lib.sr_tc_linear(_p(cur), _p(ly["W"]), _p(ly["bias"]), P, ly["n"], K, ly["n"], ly["act"], 1,
+                               _p(acts[i]) if nxt else None, Kn,
                                0.7071067811865476 if skip_next else 1.0, _p(emb) if skip_next else None,
                                d.d_in if skip_next else 0, ld, _p(out) if last else None,
                                out.shape[1] if last else 0, 0, ly["n"] if last else 0,
-                               _p(stashes[i]) if not last else None, None, 0, _p(m_dev), _stream()), "tc_linear")
-        cur, K = 1 - cur, Kn
+                               None, None, 0, 0, 1.0, _p(m_dev), _stream()), "tc_linear")
+        if nxt:
+            cur, K = acts[i], Kn
 
 
-def _tc_backward_sweep(lib, net, tcn, cot, A_bufs, P, m_dev, stashes, g_out, g_skip, n_keep):
+def _tc_backward_sweep(lib, net, tcn, cot, A_bufs, acts, P, m_dev, g_out, g_skip, n_keep):
     """cotangent rows `cot` [P][32] of the net outputs -> d/d(embedded input) in g_out [P][ld]
-    (first n_keep columns), skip-connection part in g_skip."""
+    (first n_keep columns), skip-connection part in g_skip.  acts = the forward sweep's tiles."""
     d = net.desc
     L = len(tcn.layers)
     check(lib.sr_tc_pack_rows(_p(cot), P, 32, 32, _p(A_bufs[0]), _p(m_dev), _stream()), "tc_pack_rows")
@@ -742,85 +749,164 @@ def _tc_backward_sweep(lib, net, tcn, cot, A_bufs, P, m_dev, stashes, g_out, g_s
             check(lib.sr_tc_linear(_p(A_bufs[cur]), _p(ly["Wb"]), _p(ly["zero_bias"]), P, ly["k"], K, n_prev, 0, 1,
                                    _p(A_bufs[1 - cur]), Kn, scale, None, 0, 0,
                                    _p(g_skip) if want_skip else None, g_skip.shape[1] if want_skip else 0,
-                                   n_prev, d.d_in if want_skip else 0, None, _p(stashes[l - 1]),
-                                   stashes[l - 1].shape[1], _p(m_dev), _stream()), "tc_linear")
+                                   n_prev, d.d_in if want_skip else 0, None, _p(acts[l - 1]),
+                                   _pad(ly["k"], 32), tcn.layers[l - 1]["act"], scale, _p(m_dev), _stream()),
+                  "tc_linear")
             cur, K = 1 - cur, Kn
         else:
             check(lib.sr_tc_linear(_p(A_bufs[cur]), _p(ly["Wb"]), _p(ly["zero_bias"]), P, ly["k"], K, ly["k"], 0, 1,
                                    None, 0, scale, None, 0, 0, _p(g_out), g_out.shape[1], 0, n_keep, None,
-                                   None, 0, _p(m_dev), _stream()), "tc_linear")
+                                   None, 0, 0, 1.0, _p(m_dev), _stream()), "tc_linear")
+
+
+class _TcTraceCtx:
+    """Static state of one tensor-core trace configuration: work buffers, static input / output
+    tensors and (after the second call) the captured CUDA graph of the whole trace.  Everything a
+    launch reads through a pointer lives here, so a replay only needs fresh contents copied in."""
+
+    def __init__(self, dev, P, sdf_net, def_net, n_frames, condlen, times):
+        self.B = _TcTraceBuffers(dev, P, sdf_net, def_net)
+        self.pts = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        self.rays = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        self.bi = torch.empty((P,), dtype=torch.int64, device=dev)
+        self.conds = torch.empty((n_frames, condlen), dtype=torch.float32, device=dev) if condlen else None
+        self.conv = torch.empty((P,), dtype=torch.bool, device=dev)
+        self.counters = torch.empty((times + 3,), dtype=torch.int32, device=dev)
+        self.lists = [torch.empty((P,), dtype=torch.int32, device=dev) for _ in range(2)]
+        self.lbsA = torch.empty((n_frames, 24, 4, 4), dtype=torch.float32, device=dev)
+        self.lbsT = torch.empty((n_frames, 3), dtype=torch.float32, device=dev)
+        self.lbs_params = LbsParams()
+        self.graph = None
+        self.sig = None
+        self.calls = 0
+        self.n_launches = 0
+
+
+_tc_trace_ctx = {}
+GRAPHS_ENABLED = _os.environ.get("SELFRECON_B200_GRAPHS", "1") != "0"
+
+
+def _tc_trace_body(lib, G, sdf_net, def_net, ts, td, tp, P, times, condlen, has_lbs):
+    """All launches of one trace on the current stream (eager, or under CUDA-graph capture)."""
+    B = G.B
+    ds, dd = sdf_net.desc, (def_net.desc if def_net is not None else None)
+    pw_s = (C.c_float * 16)(*[ds.pe_w[i] for i in range(16)])
+    pw_d = (C.c_float * 16)(*[dd.pe_w[i] for i in range(16)]) if dd is not None else None
+    pts, rays, bi, conds, conv, counters, lists = G.pts, G.rays, G.bi, G.conds, G.conv, G.counters, G.lists
+    lbs_ref = C.byref(G.lbs_params) if has_lbs else None
+    conv.zero_()
+    counters.zero_()
+    counters[0:1].fill_(P)
+    for it in range(times + 1):
+        idx = lists[(it + 1) & 1] if it > 0 else None
+        a_out = lists[it & 1] if it < times else None
+        m_dev = counters[it:it + 1]
+        # ---- forward sweeps (act' stashed when an update follows)
+        check(lib.sr_tc_embed(_p(pts), P, ds.multires, pw_s, 1, None, None, 0, 0, _p(B.emb_s), B.ld_s,
+                              _p(idx), _p(m_dev), _stream()), "tc_embed")
+        _tc_forward_sweep(lib, sdf_net, ts, B.emb_s, B.ld_s, B.A_in, B.acts_s, P, m_dev, B.f)
+        if def_net is not None:
+            check(lib.sr_tc_embed(_p(pts), P, dd.multires, pw_d, 1, _p(conds), _p(bi), 0, condlen,
+                                  _p(B.emb_d), B.ld_d, _p(idx), _p(m_dev), _stream()), "tc_embed")
+            _tc_forward_sweep(lib, def_net, td, B.emb_d, B.ld_d, B.A_in, B.acts_d, P, m_dev, B.off)
+        check(lib.sr_tc_trace_mid(_p(idx), _p(m_dev), P, _p(pts), _p(rays), _p(bi), _p(B.f),
+                                  _p(B.off) if def_net is not None else None, lbs_ref, C.byref(tp),
+                                  1 if a_out is not None else 0, _p(conv), _p(B.cot_s),
+                                  _p(B.cot_d) if def_net is not None else None, 32, _p(B.aux), _stream()),
+              "tc_trace_mid")
+        if a_out is None:
+            break
+        # ---- reverse sweeps + update
+        _tc_backward_sweep(lib, sdf_net, ts, B.cot_s, B.A, B.acts_s, P, m_dev, B.gs, B.gskip, ds.d_in)
+        if def_net is not None:
+            _tc_backward_sweep(lib, def_net, td, B.cot_d, B.A, B.acts_d, P, m_dev, B.gd, B.gskip,
+                               3 + 6 * dd.multires)
+        has_skip = any(l["skip"] for l in ts.layers)
+        check(lib.sr_tc_trace_update(_p(idx), _p(m_dev), P, _p(pts), _p(B.gs), B.gs.shape[1],
+                                     _p(B.gskip) if has_skip else None, B.gskip.shape[1],
+                                     _p(B.gd) if def_net is not None else None,
+                                     B.gd.shape[1] if def_net is not None else 0, _p(B.aux), ds.multires,
+                                     pw_s, dd.multires if dd is not None else 0, pw_d, _p(a_out),
+                                     _p(counters[it + 1:it + 2]), _stream()), "tc_trace_update")
 
 
 def trace_surface_points_tc(sdf_net, def_net, lbs, cam_pos, rays, init_pts, batch_inds, conds,
                             dthreshold=5e-5, athreshold=0.02, w1=3.05, w2=1.0, times=5,
                             return_counters=False):
     """OptimizeSurfacePs with the dense layers on the tensor-core engine (reverse-mode sweeps).
-    Same contract as trace_surface_points."""
+    Same contract as trace_surface_points.  A trace is ~35 launches per iteration, all with static
+    shapes and device-side counts, so from the second call with the same configuration (ray count,
+    networks, thresholds, PE weights) the whole trace is replayed as one CUDA graph
+    (SELFRECON_B200_GRAPHS=0 keeps it eager)."""
+    global LAUNCHES
     _need_cuda(rays, init_pts)
     dev = init_pts.device
     P = init_pts.shape[0]
-    pts = init_pts.detach().contiguous().float().clone()
-    rays = rays.detach().contiguous().float()
-    bi = batch_inds.contiguous().to(torch.int64) if batch_inds is not None else None
-    conds = conds.detach().contiguous().float() if conds is not None else None
-    condlen = conds.shape[-1] if conds is not None else 0
-    conv = torch.zeros((P,), dtype=torch.bool, device=dev)
-    counters = torch.zeros((times + 3,), dtype=torch.int32, device=dev)
     if P == 0:
-        return (pts, conv, counters) if return_counters else (pts, conv)
+        pts = init_pts.detach().float().clone()
+        conv = torch.zeros((0,), dtype=torch.bool, device=dev)
+        return (pts, conv, torch.zeros((times + 3,), dtype=torch.int32, device=dev)) if return_counters \
+            else (pts, conv)
     lib = _lib.load()
-    key = (dev.index, P, id(sdf_net), id(def_net))
-    B = _tc_trace_bufs.get(key)
-    if B is None:
-        _tc_trace_bufs.clear()
-        B = _TcTraceBuffers(dev, P, sdf_net, def_net)
-        _tc_trace_bufs[key] = B
+    condlen = conds.shape[-1] if conds is not None else 0
+    n_frames = lbs.A.shape[0] if lbs is not None else (conds.shape[0] if conds is not None else 1)
+    cp = tuple(float(x) for x in cam_pos.detach().view(-1).tolist())
+    ds, dd = sdf_net.desc, (def_net.desc if def_net is not None else None)
+    # buffers depend on shapes only; the captured graph also on everything a launch bakes in
+    key = (dev.index, P, tuple(ds.layer[i].n for i in range(ds.n_layers)),
+           tuple(dd.layer[i].n for i in range(dd.n_layers)) if dd is not None else (), n_frames, condlen,
+           conds.shape[0] if conds is not None else 0, times)
+    sig = (sdf_net.uid, def_net.uid if def_net is not None else -1,
+           lbs.ws_cl.data_ptr() if lbs is not None else 0, cp, float(dthreshold), float(athreshold),
+           float(w1), float(w2), tuple(ds.pe_w[i] for i in range(ds.multires)),
+           tuple(dd.pe_w[i] for i in range(dd.multires)) if dd is not None else ())
+    G = _tc_trace_ctx.get(key)
+    if G is None:
+        if len(_tc_trace_ctx) >= 4:
+            _tc_trace_ctx.pop(next(iter(_tc_trace_ctx)))
+        G = _TcTraceCtx(dev, P, sdf_net, def_net, n_frames, condlen, times)
+        _tc_trace_ctx[key] = G
+    if G.sig != sig:          # new weights / thresholds: the old graph is stale, buffers are not
+        G.sig, G.graph, G.calls = sig, None, 0
     ts, td = tc_net(sdf_net), (tc_net(def_net) if def_net is not None else None)
-    lists = [torch.empty((P,), dtype=torch.int32, device=dev) for _ in range(2)]
     tp = TraceParams()
-    cp = [float(x) for x in cam_pos.detach().view(-1).tolist()]
     for i in range(3):
         tp.cam_pos[i] = cp[i]
     tp.dthreshold, tp.athreshold, tp.w1, tp.w2 = float(dthreshold), float(athreshold), float(w1), float(w2)
-    ds, dd = sdf_net.desc, (def_net.desc if def_net is not None else None)
-    pw_s = (C.c_float * 16)(*[ds.pe_w[i] for i in range(16)])
-    pw_d = (C.c_float * 16)(*[dd.pe_w[i] for i in range(16)]) if dd is not None else None
     with torch.cuda.device(dev):
-        counters[0] = P
-        for it in range(times + 1):
-            idx = lists[(it + 1) & 1] if it > 0 else None
-            a_out = lists[it & 1] if it < times else None
-            m_dev = counters[it:it + 1]
-            # ---- forward sweeps (act' stashed when an update follows)
-            check(lib.sr_tc_embed(_p(pts), P, ds.multires, pw_s, 1, None, None, 0, 0, _p(B.emb_s), B.ld_s,
-                                  _p(idx), _p(m_dev), _stream()), "tc_embed")
-            _tc_forward_sweep(lib, sdf_net, ts, B.emb_s, B.ld_s, B.A, P, m_dev, B.f, B.ds_s)
-            if def_net is not None:
-                check(lib.sr_tc_embed(_p(pts), P, dd.multires, pw_d, 1, _p(conds), _p(bi), 0, condlen,
-                                      _p(B.emb_d), B.ld_d, _p(idx), _p(m_dev), _stream()), "tc_embed")
-                _tc_forward_sweep(lib, def_net, td, B.emb_d, B.ld_d, B.A, P, m_dev, B.off, B.ds_d)
-            check(lib.sr_tc_trace_mid(_p(idx), _p(m_dev), P, _p(pts), _p(rays), _p(bi), _p(B.f),
-                                      _p(B.off) if def_net is not None else None, _lbs_ref(lbs), C.byref(tp),
-                                      1 if a_out is not None else 0, _p(conv), _p(B.cot_s),
-                                      _p(B.cot_d) if def_net is not None else None, 32, _p(B.aux), _stream()),
-                  "tc_trace_mid")
-            if a_out is None:
-                break
-            # ---- reverse sweeps + update
-            _tc_backward_sweep(lib, sdf_net, ts, B.cot_s, B.A, P, m_dev, B.ds_s, B.gs, B.gskip, ds.d_in)
-            if def_net is not None:
-                _tc_backward_sweep(lib, def_net, td, B.cot_d, B.A, P, m_dev, B.ds_d, B.gd, B.gskip,
-                                   3 + 6 * dd.multires)
-            has_skip = any(l["skip"] for l in ts.layers)
-            check(lib.sr_tc_trace_update(_p(idx), _p(m_dev), P, _p(pts), _p(B.gs), B.gs.shape[1],
-                                         _p(B.gskip) if has_skip else None, B.gskip.shape[1],
-                                         _p(B.gd) if def_net is not None else None,
-                                         B.gd.shape[1] if def_net is not None else 0, _p(B.aux), ds.multires,
-                                         pw_s, dd.multires if dd is not None else 0, pw_d, _p(a_out),
-                                         _p(counters[it + 1:it + 2]), _stream()), "tc_trace_update")
-    if return_counters:
-        return pts, conv, counters
-    return pts, conv
+        G.pts.copy_(init_pts.detach().reshape(P, 3))
+        G.rays.copy_(rays.detach().reshape(P, 3))
+        if batch_inds is not None:
+            G.bi.copy_(batch_inds.reshape(P))
+        else:
+            G.bi.zero_()
+        if conds is not None:
+            G.conds.copy_(conds.detach())
+        if lbs is not None:
+            G.lbsA.copy_(lbs.A)
+            G.lbsT.copy_(lbs.trans)
+            C.memmove(C.byref(G.lbs_params), C.byref(lbs.params), C.sizeof(LbsParams))
+            G.lbs_params.A = G.lbsA.data_ptr()
+            G.lbs_params.trans = G.lbsT.data_ptr()
+        args = (lib, G, sdf_net, def_net, ts, td, tp, P, times, condlen, lbs is not None)
+        if G.graph is not None:
+            G.graph.replay()
+            LAUNCHES += G.n_launches
+        elif GRAPHS_ENABLED and G.calls >= 1:
+            before = LAUNCHES
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                _tc_trace_body(*args)
+            G.n_launches = LAUNCHES - before
+            G.graph = g
+            g.replay()
+        else:
+            _tc_trace_body(*args)
+        G.calls += 1
+        out = (G.pts.clone(), G.conv.clone())
+        if return_counters:
+            out = out + (G.counters.clone(),)
+    return out
 
 
 def _tc_layers_from_rows(lib, tcn, d_in, emb, ld, M, ch, n_out_last=None, skip_emb=None):
@@ -841,8 +927,8 @@ def _tc_layers_from_rows(lib, tcn, d_in, emb, ld, M, ch, n_out_last=None, skip_e
         o = torch.empty((M, nv), dtype=torch.float32, device=dev) if last else None
         check(lib.sr_tc_linear(_p(A), _p(ly["W"]), _p(ly["bias"]), M, ly["n"], K, nv, ly["act"], ch, _p(A_next), Kn,
                                0.7071067811865476 if skip_next else 1.0, _p(emb) if skip_next else None,
-                               d_in if skip_next else 0, ld, _p(o), nv if last else 0, 0, nv, None, None, 0,
-                               None, _stream()), "tc_linear")
+                               d_in if skip_next else 0, ld, _p(o), nv if last else 0, 0, nv, None, None, 0, 0,
+                               1.0, None, _stream()), "tc_linear")
         A, K, out = A_next, Kn, o
     return out
 

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+run() { name=$1; shift; echo "=== $name" ; timeout "$@" > gpurun_out/$name.log 2>&1; echo "exit $? ($name)"; tail -n 3 gpurun_out/$name.log; }
+run trace_bench 300 python tools/trace_bench.py
+run tests_trace 600 python -m pytest tests -m gpu -q -k "trace or optim or tc" --maxfail=10
