@@ -25,6 +25,7 @@
 //     the epilogue of tile i overlaps the MMAs of tile i+1.
 // The FFMA engine (mlp_kernels.cu) stays the accuracy reference; tests compare both.
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -120,7 +121,8 @@ __device__ __forceinline__ void tmem_wait(uint32_t (&v)[32]) {
 
 struct LayerArgs {
   const __nv_bfloat16* A;   // tiled activations  [MT][KC][3][128x32]
-  const __nv_bfloat16* W;   // tiled weights      [NT][KC][3][256x32]
+  const __nv_bfloat16* W;   // tiled weights      [NT][KC][planes][256x32]
+  const __nv_bfloat16* Wp;  // the same weights in the CTA-pair layout [NT][KC][half][planes][128x32]
   const float* bias;        // [NT*256]
   long long M;              // valid rows
   int MT, NT, KC;           // row tiles, col tiles, k chunks (K = 32*KC)
@@ -169,6 +171,42 @@ __device__ __forceinline__ float act_fn(float z, float& d) {
   }
 }
 
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// value only (the common epilogue: no tangent rows, no stash): 2 MUFU per softplus
+template <int ACT>
+__device__ __forceinline__ float act_val(float z) {
+  if constexpr (ACT == SR_ACT_SOFTPLUS100) {
+    // softplus(beta = 100, threshold 20): log(1 + exp(100 z)) / 100, z itself above the threshold
+    const float t = z * 144.26950408889634f;                       // 100 z log2(e)
+    const float e = fast_ex2(fminf(t, 28.853900817779268f));       // exp(min(100 z, 20))
+    const float sp = fast_lg2(1.0f + e) * 0.006931471805599453f;   // ln(2) / 100
+    return t > 28.853900817779268f ? z : sp;
+  } else if constexpr (ACT == SR_ACT_RELU) {
+    return fmaxf(z, 0.f);
+  } else if constexpr (ACT == SR_ACT_TANH) {
+    return tanhf(z);
+  } else {
+    return z;
+  }
+}
+// act'(z) recovered from the activation value a = act(z)
+template <int ACT>
+__device__ __forceinline__ float dact_from_val(float a) {
+  if constexpr (ACT == SR_ACT_SOFTPLUS100) return 1.0f - fast_ex2(a * -144.26950408889634f);
+  else if constexpr (ACT == SR_ACT_RELU) return a > 0.f ? 1.f : 0.f;
+  else if constexpr (ACT == SR_ACT_TANH) return 1.f - a * a;
+  else return 1.f;
+}
+
 // two fp32 values -> three packed bf16 pairs (element 0 in the low half = lower address)
 __device__ __forceinline__ void split3x2(float x0, float x1, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
   __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
@@ -207,7 +245,7 @@ __device__ __forceinline__ void epi_chunk(const LayerArgs& a, const EpiRow& r, u
       // a skip layer's input gradient) pass through unscaled.  ACT is the PREVIOUS layer's activation.
       const __nv_bfloat16* mt = a.mul_tiles + a_tile_off(r.mt, c0 >> 5, a.mul_KC, 0) +
                                 (size_t)(r.row_in_tile >> 3) * 64 + (r.row_in_tile & 7) * 8;
-      const float kk = -100.0f * a.mul_inv_scale;
+      const float kk = -144.26950408889634f * a.mul_inv_scale;   // -100 log2(e) / scale
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const uint4 q0 = *reinterpret_cast<const uint4*>(mt + (size_t)g * (BM * 8));
@@ -220,7 +258,7 @@ __device__ __forceinline__ void epi_chunk(const LayerArgs& a, const EpiRow& r, u
           const float as = (e & 1) ? __uint_as_float(h0 & 0xffff0000u) + __uint_as_float(h1 & 0xffff0000u)
                                    : __uint_as_float(h0 << 16) + __uint_as_float(h1 << 16);
           float d;
-          if constexpr (ACT == SR_ACT_SOFTPLUS100) d = 1.0f - __expf(kk * as);
+          if constexpr (ACT == SR_ACT_SOFTPLUS100) d = 1.0f - fast_ex2(kk * as);
           else if constexpr (ACT == SR_ACT_RELU) d = as > 0.f ? 1.f : 0.f;
           else d = 1.f;
           float val = __uint_as_float(v[j]);
@@ -237,19 +275,25 @@ __device__ __forceinline__ void epi_chunk(const LayerArgs& a, const EpiRow& r, u
         for (int jj = 0; jj < 4; ++jj) {
           const int j = j4 * 4 + jj;
           const float acc = __uint_as_float(v[j]);
-          float d = 1.f, val;
+          float val;
           if constexpr (CH == 1) {
-            val = act_fn<ACT>(acc + bb[jj], d);
+            val = act_val<ACT>(acc + bb[jj]);
           } else {
+            float d = 1.f;
             val = act_fn<ACT>(acc + bb[jj], d);                          // meaningful on value rows
             const float dv = __shfl_sync(0xffffffffu, d, r.lane & ~3);  // act'(z) of the value row
             if (!r.is_val) { val = dv * acc; }
+            v[j] = __float_as_uint(d);
           }
           o[j] = val * a.scale;
-          v[j] = __float_as_uint(d);
         }
       }
       if (a.dstash != nullptr && r.is_val && r.row_ok) {
+        if constexpr (CH == 1) {   // rarely used output: act' recomputed from the activation values
+          const float inv = 1.0f / a.scale;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(dact_from_val<ACT>(o[j] * inv));
+        }
         float4* dd = reinterpret_cast<float4*>(a.dstash + (size_t)r.row * r.ds_ld + c0);
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4)
@@ -465,6 +509,266 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(const __grid_cons
   }
 }
 
+
+// ---- CTA-pair variant (cta_group::2) ----------------------------------------------------------
+// Two CTAs of a cluster (the two SMs of a TPC) share one 256 x 256 output tile: CTA r owns rows
+// [128 r, 128 r + 128) (its own A tile and TMEM accumulator) and stages only HALF of the weight tile
+// (columns [128 r, +128)); the leader (rank 0) issues `tcgen05.mma.cta_group::2` with M = 256, which reads
+// A from each CTA's own shared memory and the two B halves from both.  Per SM that is 4 + 4 KB of operand
+// reads per MMA instead of 4 + 8 and 32 KB instead of 48 KB of TMA fill per stage -- the single-CTA
+// kernel is bound by exactly that shared-memory traffic (profiles/r01b_summary.md).
+//   barriers (each CTA's own shared memory unless noted):
+//     full[s]   own TMA bytes of stage s landed                    (producer expect_tx, count 1)
+//     pfull[s]  LEADER only: the peer's stage s landed             (remote arrive by the peer's relay thread)
+//     empty[s]  stage s consumed: leader's tcgen05.commit multicast to both CTAs
+//     tfull[b]  accumulator b complete: leader's commit multicast to both CTAs
+//     tempty[b] LEADER only: accumulator b drained by the epilogue warps of BOTH CTAs (2 x kEpiWarps)
+constexpr int P_STAGES = 6;
+constexpr int PB_PLANE = 128 * BK;                        // half weight tile plane: 128 rows x 32 k
+constexpr int PB_STAGE = kPlanes * PB_PLANE;              // 16 KB (2 planes)
+constexpr uint32_t PB_STAGE_BYTES = PB_STAGE * 2;
+constexpr size_t kSmemPair = (size_t)P_STAGES * (A_STAGE_BYTES + PB_STAGE_BYTES) + 512;
+constexpr uint32_t kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(sr_smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+// wait on a local barrier that remote CTAs (or the async proxy of the pair) arrive on.  Default (CTA-scope)
+// semantics on purpose: nothing written through the generic proxy by the partner is read here (operands
+// arrive by TMA, accumulators through TMEM + tcgen05 fences), and a cluster-scope acquire compiles to
+// MEMBAR.ALL.GPU + CCTL.IVALL in every poll -- measured 0.43 ms instead of 0.33 ms per layer.
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP_C:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE_C;\n"
+      "bra.uni WAIT_LOOP_C;\n"
+      "WAIT_DONE_C:\n"
+      "}\n" ::"r"(sr_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          sr_smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+template <int ACT, int CH, bool MUL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    tc_layer_pair_kernel(const __grid_constant__ LayerArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem);
+  __nv_bfloat16* sW = reinterpret_cast<__nv_bfloat16*>(smem + (size_t)P_STAGES * A_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)P_STAGES * (A_STAGE_BYTES + PB_STAGE_BYTES));
+  uint64_t* full = bars;                    // [P_STAGES]
+  uint64_t* pfull = bars + P_STAGES;        // [P_STAGES]  (used in the leader)
+  uint64_t* empty = bars + 2 * P_STAGES;    // [P_STAGES]
+  uint64_t* tfull = bars + 3 * P_STAGES;    // [2]
+  uint64_t* tempty = tfull + 2;             // [2]         (used in the leader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < P_STAGES; ++i) { sr_mbar_init(&full[i], 1); sr_mbar_init(&pfull[i], 1); sr_mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { sr_mbar_init(&tfull[i], 1); sr_mbar_init(&tempty[i], 2 * kEpiWarps); }
+    sr_fence_barrier_init();
+  }
+  if (warp == 1) {  // TMEM: all 512 columns in both CTAs (same warp id in both, cta_group::2)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     sr_smem_u32(tmem_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();      // barrier inits of both CTAs visible before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  long long Mrows = a.M;
+  int MTe = a.MT;
+  if (a.m_dev != nullptr) {
+    const long long md = (long long)(*a.m_dev);
+    Mrows = md < a.M ? md : a.M;
+    MTe = (int)((Mrows + BM - 1) / BM);
+  }
+  const long long npt = (long long)((MTe + 1) / 2) * a.NT;     // pair tiles (256 rows x 256 columns)
+  const long long pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      for (long long t = pair_id; t < npt; t += npairs) {
+        const long long mt = (t / a.NT) * 2 + rank;
+        const int nt = (int)(t % a.NT);
+        const bool have_a = mt < MTe;       // odd tile count: the peer's rows of the last pair do not exist
+        for (int kc = 0; kc < a.KC; ++kc) {
+          mbar_wait_cluster(&empty[slot], phase ^ 1u);
+#ifdef SR_TC_DBG_NOLOAD
+          sr_mbar_arrive(&full[slot]);
+#else
+          sr_mbar_arrive_expect_tx(&full[slot], (have_a ? A_STAGE_BYTES : 0u) + PB_STAGE_BYTES);
+          if (have_a)
+            sr_bulk_g2s(sA + (size_t)slot * A_STAGE, a.A + a_tile_off(mt, kc, a.KC, 0), A_STAGE_BYTES, &full[slot]);
+          // this CTA's half of the weight tile (columns [128 rank, +128)): one contiguous block of the pair layout
+          sr_bulk_g2s(sW + (size_t)slot * PB_STAGE,
+                      a.Wp + (((size_t)nt * a.KC + kc) * 2 + rank) * PB_STAGE, PB_STAGE_BYTES, &full[slot]);
+#endif
+          if (++slot == P_STAGES) { slot = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      if (!leader) {
+        // -------------------------------------------------------------- peer: relay "my stage landed"
+        for (long long t = pair_id; t < npt; t += npairs) {
+          for (int kc = 0; kc < a.KC; ++kc) {
+            sr_mbar_wait(&full[slot], phase);
+            mbar_arrive_remote(&pfull[slot], 0);
+            if (++slot == P_STAGES) { slot = 0; phase ^= 1u; }
+          }
+        }
+      } else {
+        // -------------------------------------------------------------- leader: MMA issuer for the pair
+        int buf = 0;
+        uint32_t bphase = 0;
+        constexpr int kTerms = kPlanes == 2 ? 3 : 6;
+        const int pa[6] = {0, 1, 0, 2, 1, 0};
+        const int pw[6] = {1, 0, 0, 0, 1, 0};
+        const int pa3[6] = {0, 2, 1, 0, 1, 0};
+        const int pw3[6] = {2, 0, 1, 1, 0, 0};
+        for (long long t = pair_id; t < npt; t += npairs) {
+          const int nt = (int)(t % a.NT);
+          (void)nt;
+          const uint32_t idesc = kIdescPair | ((uint32_t)(BN >> 3) << 17);
+          mbar_wait_cluster(&tempty[buf], bphase ^ 1u);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)buf * BN;
+          uint32_t accumulate = 0;
+          for (int kc = 0; kc < a.KC; ++kc) {
+            sr_mbar_wait(&full[slot], phase);
+#ifndef SR_TC_DBG_NOPFULL   // tuning knock-out: do not wait for the peer's stage
+            mbar_wait_cluster(&pfull[slot], phase);
+#endif
+            tc_fence_after();
+            const uint32_t abase = sr_smem_u32(sA + (size_t)slot * A_STAGE);
+            const uint32_t wbase = sr_smem_u32(sW + (size_t)slot * PB_STAGE);
+#ifdef SR_TC_DBG_NOMMA
+            if (kc == 0)
+#endif
+#pragma unroll
+            for (int q = 0; q < kTerms; ++q) {
+#pragma unroll
+              for (int j = 0; j < BK / 16; ++j) {
+                const int qa = kPlanes == 2 ? pa[q] : pa3[q], qw = kPlanes == 2 ? pw[q] : pw3[q];
+                const uint64_t ad = make_desc(abase + qa * (A_PLANE * 2) + j * 2 * (BM * 16), BM * 16, 128);
+                const uint64_t bd = make_desc(wbase + qw * (PB_PLANE * 2) + j * 2 * (128 * 16), 128 * 16, 128);
+                mma_bf16_pair(tmem_d, ad, bd, idesc, accumulate);
+                accumulate = 1;
+              }
+            }
+            mma_commit_pair(&empty[slot]);
+            if (++slot == P_STAGES) { slot = 0; phase ^= 1u; }
+          }
+          mma_commit_pair(&tfull[buf]);
+          if (++buf == 2) { buf = 0; bphase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    EpiRow r;
+    r.row_in_tile = q * 32 + lane;
+    r.lane = lane;
+    r.is_val = (CH == 1) || ((lane & 3) == 0);
+    r.ds_ld = (size_t)a.NT * BN;
+    int buf = 0;
+    uint32_t bphase = 0;
+    for (long long t = pair_id; t < npt; t += npairs) {
+      r.mt = (t / a.NT) * 2 + rank;
+      r.nt = (int)(t % a.NT);
+      r.row = r.mt * BM + r.row_in_tile;
+      r.row_ok = r.row < Mrows;
+#ifdef SR_TC_DBG_NOEPI
+      const bool have_rows = false;
+#else
+      const bool have_rows = r.mt < MTe;
+#endif
+      const int c_base = r.nt * BN + half * 128;
+      const int n_live = have_rows ? (a.n_gemm - c_base + 31) >> 5 : 0;
+      mbar_wait_cluster(&tfull[buf], bphase);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * BN + half * 128;
+      if (!have_rows) {
+        // phantom row tile of an odd tile count: nothing to read or write
+      } else if constexpr (CH == 1 && !MUL) {
+        uint32_t va[32], vb[32];
+        if (n_live > 0) tmem_ld32_async(taddr0, va);
+#pragma unroll
+        for (int i = 0; i < 4; i += 2) {
+          if (i < n_live) tmem_wait(va);
+          if (i + 1 < n_live) tmem_ld32_async(taddr0 + (i + 1) * 32, vb);
+          epi_chunk<ACT, CH, MUL>(a, r, va, half * 4 + i, i < n_live);
+          if (i + 1 < n_live) tmem_wait(vb);
+          if (i + 2 < 4 && i + 2 < n_live) tmem_ld32_async(taddr0 + (i + 2) * 32, va);
+          epi_chunk<ACT, CH, MUL>(a, r, vb, half * 4 + i + 1, i + 1 < n_live);
+        }
+      } else {
+        for (int i = 0; i < 4; ++i) {
+          uint32_t v[32];
+          if (i < n_live) { tmem_ld32_async(taddr0 + i * 32, v); tmem_wait(v); }
+          epi_chunk<ACT, CH, MUL>(a, r, v, half * 4 + i, i < n_live);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&tempty[buf], 0);   // the leader's barrier counts both CTAs' warps
+      if (++buf == 2) { buf = 0; bphase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();      // no CTA leaves (or frees TMEM) while its partner may still touch it
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // ---- packing kernels -------------------------------------------------------------------------
 // fp32 row-major [M][K] (ld) -> tiled bf16x3 activations with KC = ceil(Kpad/32) chunks
 __global__ void pack_rows_kernel(const float* __restrict__ src, long long M, int K, int ld,
@@ -521,6 +825,12 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int N, int K, i
     const size_t off = (size_t)k8 * (BN * 8) + (size_t)(r >> 3) * 64 + (r & 7) * 8;
     *reinterpret_cast<uint4*>(dst + w_tile_off(nt, kc, KC, 0) + off) = *reinterpret_cast<uint4*>(p1);
     *reinterpret_cast<uint4*>(dst + w_tile_off(nt, kc, KC, 1) + off) = *reinterpret_cast<uint4*>(p2);
+    // second copy in the CTA-pair layout: [nt][kc][half][plane][k8][128 rows][8]
+    __nv_bfloat16* dp = dst + (size_t)NT * KC * W_STAGE + (((size_t)nt * KC + kc) * 2 + (r >> 7)) * PB_STAGE +
+                        (size_t)k8 * (128 * 8) + (size_t)((r & 127) >> 3) * 64 + (r & 7) * 8;
+    *reinterpret_cast<uint4*>(dp) = *reinterpret_cast<uint4*>(p1);
+    *reinterpret_cast<uint4*>(dp + PB_PLANE) = *reinterpret_cast<uint4*>(p2);
+    if constexpr (kPlanes == 3) *reinterpret_cast<uint4*>(dp + 2 * PB_PLANE) = *reinterpret_cast<uint4*>(p3);
     if constexpr (kPlanes == 3)
       *reinterpret_cast<uint4*>(dst + w_tile_off(nt, kc, KC, kPlanes - 1) + off) = *reinterpret_cast<uint4*>(p3);
   }
@@ -604,7 +914,7 @@ int64_t sr_tc_act_bytes(int64_t M, int K) {
 }
 int64_t sr_tc_weight_bytes(int N, int K) {
   const int64_t NT = (N + sr_tc::BN - 1) / sr_tc::BN, KC = (K + 31) / 32;
-  return NT * KC * sr_tc::kPlanes * sr_tc::W_PLANE * 2;
+  return 2 * NT * KC * sr_tc::kPlanes * sr_tc::W_PLANE * 2;   // single-CTA layout + CTA-pair layout
 }
 
 int sr_tc_pack_rows(const float* src, int64_t M, int K, int ld, void* dst, const int32_t* m_dev,
@@ -636,6 +946,7 @@ int sr_tc_linear(const void* A, const void* W, const float* bias, int64_t M, int
   LayerArgs a;
   a.A = (const __nv_bfloat16*)A; a.W = (const __nv_bfloat16*)W; a.bias = bias; a.M = M;
   a.MT = (int)((M + BM - 1) / BM); a.NT = (N + BN - 1) / BN; a.KC = (K + 31) / 32;
+  a.Wp = a.W + (size_t)a.NT * a.KC * W_STAGE;
   a.n_gemm = N; a.n = n_valid; a.ch = ch;
   a.A_next = (__nv_bfloat16*)A_next; a.KCn = A_next ? (K_next + 31) / 32 : 0;
   a.scale = scale; a.skip_src = skip_src; a.skip_n = skip_n; a.skip_ld = skip_ld;
@@ -644,46 +955,62 @@ int sr_tc_linear(const void* A, const void* W, const float* bias, int64_t M, int
   a.mul_inv_scale = mul_scale != 0.f ? 1.0f / mul_scale : 1.0f; a.m_dev = m_dev;
   if (mul_tiles && (ch != 1 || mul_K < n_valid)) return SR_EINVAL;
   using Kern = void (*)(const LayerArgs);
+  static const int use_pair = [] { const char* e = getenv("SELFRECON_B200_TC_PAIR"); return e ? atoi(e) : 1; }();
+  // the pair kernel always issues N = 256 MMAs (a narrower N would take columns from BOTH halves)
+  const bool pair = use_pair && a.MT >= 2 && (N % BN == 0);
+#define SR_TC_PICK(ACT_, CH_, MUL_) \
+  (pair ? (Kern)tc_layer_pair_kernel<ACT_, CH_, MUL_> : (Kern)tc_layer_kernel<ACT_, CH_, MUL_>)
   Kern kern = nullptr;
   if (mul_tiles) {
     switch (mul_act) {
-      case SR_ACT_NONE: kern = tc_layer_kernel<SR_ACT_NONE, 1, true>; break;
-      case SR_ACT_SOFTPLUS100: kern = tc_layer_kernel<SR_ACT_SOFTPLUS100, 1, true>; break;
-      case SR_ACT_RELU: kern = tc_layer_kernel<SR_ACT_RELU, 1, true>; break;
+      case SR_ACT_NONE: kern = SR_TC_PICK(SR_ACT_NONE, 1, true); break;
+      case SR_ACT_SOFTPLUS100: kern = SR_TC_PICK(SR_ACT_SOFTPLUS100, 1, true); break;
+      case SR_ACT_RELU: kern = SR_TC_PICK(SR_ACT_RELU, 1, true); break;
     }
   } else if (ch == 1) {
     switch (act) {
-      case SR_ACT_NONE: kern = tc_layer_kernel<SR_ACT_NONE, 1, false>; break;
-      case SR_ACT_SOFTPLUS100: kern = tc_layer_kernel<SR_ACT_SOFTPLUS100, 1, false>; break;
-      case SR_ACT_RELU: kern = tc_layer_kernel<SR_ACT_RELU, 1, false>; break;
-      case SR_ACT_TANH: kern = tc_layer_kernel<SR_ACT_TANH, 1, false>; break;
+      case SR_ACT_NONE: kern = SR_TC_PICK(SR_ACT_NONE, 1, false); break;
+      case SR_ACT_SOFTPLUS100: kern = SR_TC_PICK(SR_ACT_SOFTPLUS100, 1, false); break;
+      case SR_ACT_RELU: kern = SR_TC_PICK(SR_ACT_RELU, 1, false); break;
+      case SR_ACT_TANH: kern = SR_TC_PICK(SR_ACT_TANH, 1, false); break;
     }
   } else {
     switch (act) {
-      case SR_ACT_NONE: kern = tc_layer_kernel<SR_ACT_NONE, 4, false>; break;
-      case SR_ACT_SOFTPLUS100: kern = tc_layer_kernel<SR_ACT_SOFTPLUS100, 4, false>; break;
-      case SR_ACT_RELU: kern = tc_layer_kernel<SR_ACT_RELU, 4, false>; break;
-      case SR_ACT_TANH: kern = tc_layer_kernel<SR_ACT_TANH, 4, false>; break;
+      case SR_ACT_NONE: kern = SR_TC_PICK(SR_ACT_NONE, 4, false); break;
+      case SR_ACT_SOFTPLUS100: kern = SR_TC_PICK(SR_ACT_SOFTPLUS100, 4, false); break;
+      case SR_ACT_RELU: kern = SR_TC_PICK(SR_ACT_RELU, 4, false); break;
+      case SR_ACT_TANH: kern = SR_TC_PICK(SR_ACT_TANH, 4, false); break;
     }
   }
+#undef SR_TC_PICK
   if (!kern) return SR_EINVAL;
   static bool attr_set = false;
   if (!attr_set) {
-    Kern all[] = {tc_layer_kernel<SR_ACT_NONE, 1, true>,          tc_layer_kernel<SR_ACT_SOFTPLUS100, 1, true>,
-                  tc_layer_kernel<SR_ACT_RELU, 1, true>,          tc_layer_kernel<SR_ACT_NONE, 1, false>,
-                  tc_layer_kernel<SR_ACT_SOFTPLUS100, 1, false>,  tc_layer_kernel<SR_ACT_RELU, 1, false>,
-                  tc_layer_kernel<SR_ACT_TANH, 1, false>,         tc_layer_kernel<SR_ACT_NONE, 4, false>,
-                  tc_layer_kernel<SR_ACT_SOFTPLUS100, 4, false>,  tc_layer_kernel<SR_ACT_RELU, 4, false>,
-                  tc_layer_kernel<SR_ACT_TANH, 4, false>};
-    for (Kern k : all) {
-      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
-      if (e != cudaSuccess) return (int)e;
-    }
+#define SR_TC_BOTH(ACT_, CH_, MUL_)                                                                        \
+  {                                                                                                        \
+    cudaError_t e1 = cudaFuncSetAttribute(tc_layer_kernel<ACT_, CH_, MUL_>,                                \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);        \
+    cudaError_t e2 = cudaFuncSetAttribute(tc_layer_pair_kernel<ACT_, CH_, MUL_>,                           \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPair);    \
+    if (e1 != cudaSuccess) return (int)e1;                                                                 \
+    if (e2 != cudaSuccess) return (int)e2;                                                                 \
+  }
+    SR_TC_BOTH(SR_ACT_NONE, 1, true) SR_TC_BOTH(SR_ACT_SOFTPLUS100, 1, true) SR_TC_BOTH(SR_ACT_RELU, 1, true)
+    SR_TC_BOTH(SR_ACT_NONE, 1, false) SR_TC_BOTH(SR_ACT_SOFTPLUS100, 1, false) SR_TC_BOTH(SR_ACT_RELU, 1, false)
+    SR_TC_BOTH(SR_ACT_TANH, 1, false) SR_TC_BOTH(SR_ACT_NONE, 4, false) SR_TC_BOTH(SR_ACT_SOFTPLUS100, 4, false)
+    SR_TC_BOTH(SR_ACT_RELU, 4, false) SR_TC_BOTH(SR_ACT_TANH, 4, false)
+#undef SR_TC_BOTH
     attr_set = true;
   }
-  const long long ntiles = (long long)a.MT * a.NT;
-  const int grid = (int)(ntiles < SR_NUM_SMS_B200 ? ntiles : SR_NUM_SMS_B200);
-  kern<<<grid, kThreads, kSmem, s>>>(a);
+  if (pair) {
+    const long long npt = (long long)((a.MT + 1) / 2) * a.NT;
+    const long long npairs = npt < SR_NUM_SMS_B200 / 2 ? npt : SR_NUM_SMS_B200 / 2;
+    kern<<<(unsigned)(2 * npairs), kThreads, kSmemPair, s>>>(a);
+  } else {
+    const long long ntiles = (long long)a.MT * a.NT;
+    const int grid = (int)(ntiles < SR_NUM_SMS_B200 ? ntiles : SR_NUM_SMS_B200);
+    kern<<<grid, kThreads, kSmem, s>>>(a);
+  }
   return sr_launch_status();
 }
 }

@@ -5,5 +5,5 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from selfreconcode_b200 import build
 for tag, defs in [("noepi", ["SR_TC_DBG_NOEPI"]), ("nomma", ["SR_TC_DBG_NOMMA"]), ("noload", ["SR_TC_DBG_NOLOAD"]),
-                  ("planes3", ["SR_TC_PLANES=3"])]:
+                  ("nopfull", ["SR_TC_DBG_NOPFULL"]), ("noload_noepi", ["SR_TC_DBG_NOLOAD", "SR_TC_DBG_NOEPI"])]:
     print(tag, build.build_variant(tag, defs))
