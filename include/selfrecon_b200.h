@@ -332,6 +332,18 @@ int sr_tc_render_embed(int64_t P, const float* pts, const float* views, const fl
 int sr_seg3d_candidates(const uint8_t* flag, const uint8_t* calculated, uint8_t* cand, int D,
                         int H, int W, int sz, int sy, int sx, int fD, int fH, int fW,
                         cudaStream_t s);
+/* Per-pass glue around the query function (seg3d_lossless.py:94-101, 318-346):
+ *   gather : lin[n] (linear ids on the [D,H,W] level lattice) -> world points [n,3] with
+ *            batch_eval's arithmetic (c/res + (1/res)/2) * (bmax-bmin) + bmin, one rounding per
+ *            op; interp[n] = grid[lin]; calculated[final-grid voxel] = 1.  bmin/bmax: HOST [3].
+ *   scatter: grid[lin] = values; conflict[lin] = (interp-balance)*(values-balance) < 0 on a
+ *            zeroed level-sized byte mask; *n_conflicts = how many (device int32). */
+int sr_seg3d_gather(const int64_t* lin, int64_t n, int H, int W, int sz, int sy, int sx, int fD,
+                    int fH, int fW, const float* bmin, const float* bmax, const float* grid,
+                    float* points, float* interp, uint8_t* calculated, cudaStream_t s);
+int sr_seg3d_scatter(const int64_t* lin, int64_t n, const float* values, const float* interp,
+                     float balance, float* grid, uint8_t* conflict, int64_t conflict_bytes,
+                     int32_t* n_conflicts, cudaStream_t s);
 
 #ifdef __cplusplus
 }

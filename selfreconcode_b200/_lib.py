@@ -109,6 +109,9 @@ SIGNATURES = {
                                      i32, stream_t]),
     "sr_seg3d_candidates": (C.c_int, [c_f, c_f, c_f, i32, i32, i32, i32, i32, i32, i32, i32, i32,
                                       stream_t]),
+    "sr_seg3d_gather": (C.c_int, [c_f, i64, i32, i32, i32, i32, i32, i32, i32, i32, C.POINTER(f32), C.POINTER(f32),
+                                  c_f, c_f, c_f, c_f, stream_t]),
+    "sr_seg3d_scatter": (C.c_int, [c_f, i64, c_f, c_f, f32, c_f, c_f, i64, c_f, stream_t]),
 }
 
 _lib = None

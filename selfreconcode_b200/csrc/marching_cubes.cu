@@ -116,6 +116,7 @@ struct McLayout {
   long long nwords;
   int nctas;
   uint32_t *fx, *fy, *fz, *vpre, *tpre;  // [nwords]
+  uint32_t* sgn;                         // [nwords] bit k of word (i,j,k/32): sdf[i,j,k] < iso
   uint32_t *cta_v, *cta_t;               // [nctas] totals -> exclusive prefix (in place)
 };
 
@@ -136,6 +137,7 @@ __host__ McLayout make_layout(int nx, int ny, int nz, void* work) {
   L.fz = (uint32_t*)p; p += wb;
   L.vpre = (uint32_t*)p; p += wb;
   L.tpre = (uint32_t*)p; p += wb;
+  L.sgn = (uint32_t*)p; p += wb;
   long long cb = align_up((long long)L.nctas * 4, 256);
   L.cta_v = (uint32_t*)p; p += cb;
   L.cta_t = (uint32_t*)p; p += cb;
@@ -203,58 +205,91 @@ __device__ __forceinline__ int load_cube(const float* __restrict__ sdf, int nx, 
   return cube_index(c, nx, ny, nz, i, j, k, iso, v);
 }
 
+// ---- classification in two passes -------------------------------------------------------------
+// Pass 1 (HBM bound, the only full read of the grid): one warp per 32 samples of a z-row, one
+// coalesced 128-byte load, `v < iso` balloted into a sign bit-plane (1 bit per sample).
+// Pass 2 (one THREAD per 32-cell word): the eight corner bit-words of the word's cells are the sign
+// words of rows (i,j) (i+1,j) (i+1,j+1) (i,j+1) and the same shifted by one k; crossed-edge flags are
+// XORs of whole words, active cells are where the eight words disagree, and only those cells (a few
+// per cent) index the triangle table.  The first version computed a cube index per lane from eight
+// float loads and was issue bound at 4 % of HBM (profiles/r01b_summary.md).
+constexpr int kSignWordsPerWarp = 8;
 __global__ void __launch_bounds__(kThreads)
-mc_classify_kernel(const float* __restrict__ sdf, McLayout L, float iso) {
-  __shared__ uint32_t s_wv[kWarps], s_wt[kWarps];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long word0 = (long long)blockIdx.x * kWordsPerCta + (long long)warp * kWordsPerWarp;
-  uint32_t my_nv = 0, my_nt = 0;  // lane `it` keeps the counts of word0+it
-  // (i, j, kw) of the warp's first word, then advanced incrementally: the per-word 64-bit
-  // div/mod of the first version made the kernel issue-bound (ncu: SM 72 %, DRAM 5 %).
-  int kw = (int)((uint32_t)word0 % (uint32_t)L.nwz);
-  uint32_t ij0 = (uint32_t)word0 / (uint32_t)L.nwz;
-  int j = (int)(ij0 % (uint32_t)L.ny), i = (int)(ij0 / (uint32_t)L.ny);
-  CubeLoads cur = cube_loads(sdf, L.nx, L.ny, L.nz, min(i, L.nx - 1), j, kw * 32 + lane);
-  for (int it = 0; it < kWordsPerWarp; ++it) {
-    const long long word = word0 + it;
-    // coordinates of the next word + its loads, issued before this word is reduced
-    int nkw = kw + 1, nj = j, ni = i;
-    if (nkw == L.nwz) { nkw = 0; if (++nj == L.ny) { nj = 0; ++ni; } }
-    CubeLoads nxt = cur;
-    if (it + 1 < kWordsPerWarp && word + 1 < L.nwords)
-      nxt = cube_loads(sdf, L.nx, L.ny, L.nz, ni, nj, nkw * 32 + lane);
-    uint32_t fx = 0, fy = 0, fz = 0;
-    int nt = 0;
-    if (word < L.nwords) {  // warp-uniform
-      const int k = kw * 32 + lane;
-      float v[8];
-      const int idx = cube_index(cur, L.nx, L.ny, L.nz, i, j, k, iso, v);
-      bool ex = false, ey = false, ez = false;
-      int t = 0;
-      if (idx > 0 && idx < 255) {
-        ex = ((idx ^ (idx >> 1)) & 1) != 0;  // c0-c1
-        ey = ((idx ^ (idx >> 3)) & 1) != 0;  // c3-c0
-        ez = ((idx ^ (idx >> 4)) & 1) != 0;  // c0-c4
-        t = tri_count(kTriPacked[idx]);
-      }
-      fx = __ballot_sync(0xffffffffu, ex);
-      fy = __ballot_sync(0xffffffffu, ey);
-      fz = __ballot_sync(0xffffffffu, ez);
-      // triangle counts are 0..5: three ballots + popc instead of a 5-step shuffle reduction
-      nt = __popc(__ballot_sync(0xffffffffu, t & 1)) + 2 * __popc(__ballot_sync(0xffffffffu, t & 2)) +
-           4 * __popc(__ballot_sync(0xffffffffu, t & 4));
-      if (lane == 0) {
-        L.fx[word] = fx; L.fy[word] = fy; L.fz[word] = fz;
-      }
-    }
-    if (lane == it) {
-      my_nv = __popc(fx) + __popc(fy) + __popc(fz);
-      my_nt = (uint32_t)nt;
-    }
-    cur = nxt; kw = nkw; j = nj; i = ni;
+mc_sign_kernel(const float* __restrict__ sdf, McLayout L, float iso) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
+  const long long w0 = warp * kSignWordsPerWarp;
+  if (w0 >= L.nwords) return;
+  uint32_t row = (uint32_t)(w0 / (uint32_t)L.nwz);
+  int kw = (int)(w0 - (long long)row * L.nwz);
+  float v[kSignWordsPerWarp];
+  bool in[kSignWordsPerWarp];
+  uint32_t r = row;
+  int q = kw;
+#pragma unroll
+  for (int u = 0; u < kSignWordsPerWarp; ++u) {   // all loads first: 8 independent 128-byte rows in flight
+    const int k = q * 32 + lane;
+    in[u] = (w0 + u < L.nwords) && k < L.nz;
+    v[u] = in[u] ? __ldg(sdf + (size_t)r * L.nz + k) : 0.f;
+    if (++q == L.nwz) { q = 0; ++r; }
   }
-  // warp-inclusive scan over the 32 words of this warp
-  uint32_t sv = my_nv, st = my_nt;
+#pragma unroll
+  for (int u = 0; u < kSignWordsPerWarp; ++u) {
+    const uint32_t bits = __ballot_sync(0xffffffffu, in[u] && v[u] < iso);
+    if (lane == 0 && w0 + u < L.nwords) L.sgn[w0 + u] = bits;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+mc_classify_kernel(McLayout L) {
+  __shared__ uint64_t s_tri[256];
+  __shared__ uint32_t s_wv[kWarps], s_wt[kWarps];
+  s_tri[threadIdx.x] = kTriPacked[threadIdx.x];   // kThreads == 256
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long word = (long long)blockIdx.x * kWordsPerCta + threadIdx.x;
+  uint32_t fx = 0, fy = 0, fz = 0, nv = 0, nt = 0;
+  if (word < L.nwords) {
+    const uint32_t row = (uint32_t)(word / (uint32_t)L.nwz);
+    const int kw = (int)(word - (long long)row * L.nwz);
+    const int j = (int)(row % (uint32_t)L.ny), i = (int)(row / (uint32_t)L.ny);
+    if (i < L.nx - 1 && j < L.ny - 1) {
+      // cells of this word: k = 32 kw + b, valid while k < nz - 1
+      const int rem = L.nz - 1 - kw * 32;
+      const uint32_t cellmask = rem >= 32 ? 0xffffffffu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
+      const bool more = kw + 1 < L.nwz;
+      const uint32_t* p0 = L.sgn + word;                       // row (i, j)
+      const uint32_t* p1 = p0 + (size_t)L.ny * L.nwz;          // row (i+1, j)
+      const uint32_t* p2 = p1 + L.nwz;                         // row (i+1, j+1)
+      const uint32_t* p3 = p0 + L.nwz;                         // row (i, j+1)
+      const uint32_t a0 = p0[0], a1 = p1[0], a2 = p2[0], a3 = p3[0];
+      const uint32_t n0 = more ? p0[1] : 0u, n1 = more ? p1[1] : 0u, n2 = more ? p2[1] : 0u,
+                     n3 = more ? p3[1] : 0u;
+      // corner bit-words: c0 000, c1 100, c2 110, c3 010 at k; c4..c7 the same rows at k+1
+      const uint32_t c[8] = {a0, a1, a2, a3, (a0 >> 1) | (n0 << 31), (a1 >> 1) | (n1 << 31),
+                             (a2 >> 1) | (n2 << 31), (a3 >> 1) | (n3 << 31)};
+      const uint32_t all_or = c[0] | c[1] | c[2] | c[3] | c[4] | c[5] | c[6] | c[7];
+      const uint32_t all_and = c[0] & c[1] & c[2] & c[3] & c[4] & c[5] & c[6] & c[7];
+      uint32_t active = cellmask & all_or & ~all_and;
+      fx = (c[0] ^ c[1]) & cellmask;   // edge c0-c1 (+x)
+      fy = (c[0] ^ c[3]) & cellmask;   // edge c3-c0 (+y)
+      fz = (c[0] ^ c[4]) & cellmask;   // edge c0-c4 (+z)
+      nv = __popc(fx) + __popc(fy) + __popc(fz);
+      while (active) {
+        const int b = __ffs(active) - 1;
+        active &= active - 1;
+        int idx = 0;
+#pragma unroll
+        for (int qq = 0; qq < 8; ++qq) idx |= ((c[qq] >> b) & 1u) << qq;
+        nt += tri_count(s_tri[idx]);
+      }
+      L.fx[word] = fx; L.fy[word] = fy; L.fz[word] = fz;
+    } else {
+      L.fx[word] = 0; L.fy[word] = 0; L.fz[word] = 0;
+    }
+  }
+  // CTA-exclusive prefixes of the vertex / triangle counts over the 256 words of this CTA
+  uint32_t sv = nv, st = nt;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     uint32_t a = __shfl_up_sync(0xffffffffu, sv, o);
@@ -265,10 +300,9 @@ mc_classify_kernel(const float* __restrict__ sdf, McLayout L, float iso) {
   __syncthreads();
   uint32_t bv = 0, bt = 0;
   for (int w = 0; w < warp; ++w) { bv += s_wv[w]; bt += s_wt[w]; }
-  const long long word = word0 + lane;
   if (word < L.nwords) {
-    L.vpre[word] = bv + sv - my_nv;
-    L.tpre[word] = (bt + st - my_nt) | (my_nt ? kHasTris : 0u);
+    L.vpre[word] = bv + sv - nv;
+    L.tpre[word] = (bt + st - nt) | (nt ? kHasTris : 0u);
   }
   if (threadIdx.x == kThreads - 1) {
     L.cta_v[blockIdx.x] = bv + sv;
@@ -356,15 +390,16 @@ mc_emit_kernel(const float* __restrict__ sdf, McLayout L, float iso, float xs, f
       wfx = L.fx[w]; wfy = L.fy[w]; wfz = L.fz[w]; wv = L.vpre[w]; wt = L.tpre[w];
     }
   }
-  for (int it = 0; it < kWordsPerWarp; ++it) {
+  // words that own a vertex or hold faces (a word can hold faces but own no vertex: all its crossed
+  // edges belong to neighbours, hence the separate has-triangles bit); the rest cost nothing
+  uint32_t todo = __ballot_sync(0xffffffffu, (wfx | wfy | wfz) != 0u || (wt & kHasTris) != 0u);
+  while (todo) {
+    const int it = __ffs(todo) - 1;
+    todo &= todo - 1;
     const long long word = word0 + it;
-    if (word >= L.nwords) break;
     const uint32_t fx = __shfl_sync(0xffffffffu, wfx, it), fy = __shfl_sync(0xffffffffu, wfy, it),
                    fz = __shfl_sync(0xffffffffu, wfz, it);
     const uint32_t tp = __shfl_sync(0xffffffffu, wt, it);
-    // A word can hold faces but own no vertex (all its crossed edges belong to
-    // neighbours), hence the separate has-triangles bit.
-    if ((fx | fy | fz) == 0u && (tp & kHasTris) == 0u) continue;
     const uint32_t vbase = cta_v + __shfl_sync(0xffffffffu, wv, it);
     const uint32_t tbase = cta_t + (tp & ~kHasTris);
     const int kw = (int)((uint32_t)word % (uint32_t)L.nwz);
@@ -443,7 +478,7 @@ int64_t sr_mc_work_bytes(int nx, int ny, int nz) {
   long long nwz = (nz + 31) / 32;
   long long nwords = (long long)nx * ny * nwz;
   long long nctas = (nwords + kWordsPerCta - 1) / kWordsPerCta;
-  return 5 * align_up(nwords * 4, 256) + 2 * align_up(nctas * 4, 256);
+  return 6 * align_up(nwords * 4, 256) + 2 * align_up(nctas * 4, 256);
 }
 
 int sr_mc_count(const float* sdf, int nx, int ny, int nz, float iso, void* work, int32_t* counts,
@@ -451,7 +486,11 @@ int sr_mc_count(const float* sdf, int nx, int ny, int nz, float iso, void* work,
   if (nx <= 0 || ny <= 0 || nz <= 0 || !sdf || !work || !counts) return SR_EINVAL;
   if ((long long)nx * ny * nz > 0x7fffffffLL) return SR_EUNSUPPORTED;
   McLayout L = make_layout(nx, ny, nz, work);
-  mc_classify_kernel<<<L.nctas, kThreads, 0, s>>>(sdf, L, iso);
+  {
+    const long long warps = (L.nwords + kSignWordsPerWarp - 1) / kSignWordsPerWarp;
+    mc_sign_kernel<<<(unsigned)((warps + kWarps - 1) / kWarps), kThreads, 0, s>>>(sdf, L, iso);
+  }
+  mc_classify_kernel<<<L.nctas, kThreads, 0, s>>>(L);
   mc_scan_kernel<<<1, 1024, 0, s>>>(L, counts);
   return sr_launch_status();
 }

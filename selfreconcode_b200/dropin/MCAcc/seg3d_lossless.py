@@ -9,6 +9,10 @@ dilate by one, drop what was already evaluated, query the function there, and re
 conflicts by querying the 27-neighbourhoods until none remain.  The plumbing differs:
 
   * upsample + boundary flag: one kernel (csrc/interp2x.cu) instead of two F.interpolate calls;
+  * per pass, the lattice -> world arithmetic of batch_eval, the gather of interpolated values, the
+    `calculated` update, the write-back and the conflict test are two kernels (csrc/seg3d.cu) instead
+    of ~25 torch launches; the only host round trips left are the candidate count and the conflict
+    count;
   * dilation + "already evaluated" mask: one byte kernel (csrc/seg3d.cu) over the strided view
     of the final-grid `calculated` mask -- the reference keeps a coordinate list made unique by a
     sort at every step (seg3d_lossless.py:343-346) and dilates with an fp32 conv3d (:296);
@@ -80,12 +84,6 @@ class Seg3dLossless(nn.Module):
     def forward(self, **kwargs):
         return self._forward(**kwargs)
 
-    def _lattice_coords(self, lin, H, W, stride):
-        z = lin // (H * W)
-        y = (lin // W) % H
-        x = lin % W
-        return torch.stack([x * stride[0], y * stride[1], z * stride[2]], dim=1).unsqueeze(0)
-
     def _forward(self, **kwargs):
         dev = self.b_min.device
         if dev.type != "cuda":
@@ -93,13 +91,14 @@ class Seg3dLossless(nn.Module):
         fW, fH, fD = [int(v) for v in self.resolutions[-1]]
         calculated = torch.zeros((fD, fH, fW), dtype=torch.bool, device=dev)
         bal = self.balance_value
+        bmin = [float(v) for v in self.b_min.view(-1).tolist()]
+        bmax = [float(v) for v in self.b_max.view(-1).tolist()]
         nq = 0
         occ = None
         for li, resolution in enumerate(self.resolutions):
             W, H, D = [int(v) for v in resolution]
             stride = (self.resolutions[-1] - 1) // (resolution - 1)  # (sx, sy, sz)
             sx, sy, sz = [int(v) for v in stride]
-            stride_dev = stride.to(dev)
             if li == 0:
                 coords = self.init_coords.clone()
                 occ = self.batch_eval(coords, **kwargs).view(D, H, W).float()
@@ -117,18 +116,16 @@ class Seg3dLossless(nn.Module):
                 lin = cand.view(-1).nonzero().view(-1)
                 if lin.numel() == 0:
                     break
-                coords = self._lattice_coords(lin, H, W, stride_dev)
-                interp = flat[lin]
-                true = self.batch_eval(coords, **kwargs).view(-1).float()
-                flat[lin] = true
-                c = coords[0]
-                calculated[c[:, 2], c[:, 1], c[:, 0]] = True
+                # lattice ids -> world points (batch_eval's arithmetic), interpolated values, calculated[] = 1
+                points, interp = ops.seg3d_gather(lin, (H, W), (sz, sy, sx), calculated, bmin, bmax, flat)
+                true = self.query_func(**kwargs, points=points.view(1, -1, 3))
+                if type(true) is list:
+                    true = torch.stack(true)
+                true = true.reshape(-1).float().contiguous()
+                conflicts, ncf = ops.seg3d_scatter(lin, true, interp, bal, flat)
                 nq += lin.numel()
-                conflicts = (interp - bal) * (true - bal) < 0
-                if not bool(conflicts.any()):
+                if int(ncf.item()) == 0:
                     break
-                flag = torch.zeros((D * H * W,), dtype=torch.bool, device=dev)
-                flag[lin[conflicts]] = True
-                flag = flag.view(D, H, W)
+                flag = conflicts.view(D, H, W)
         self.last_num_queried = nq
         return occ.view(1, 1, *occ.shape)

@@ -26,7 +26,7 @@ import itertools as _it
 _uid_counter = _it.count()
 LAUNCHES = 0  # kernels launched by this module since it was last reset (bench.py reads it)
 
-_KERNELS_PER_CALL = {"mc_count": 2}
+_KERNELS_PER_CALL = {"mc_count": 3}
 
 
 def _stream():
@@ -539,6 +539,41 @@ def seg3d_candidates(flag, calculated, stride_zyx):
                                       int(stride_zyx[0]), int(stride_zyx[1]), int(stride_zyx[2]),
                                       fD, fH, fW, _stream()), "seg3d_candidates")
     return cand
+
+
+_KERNELS_PER_CALL.update({"seg3d_candidates": 2, "seg3d_scatter": 3})
+
+
+def seg3d_gather(lin, level_hw, stride_zyx, calculated, bmin, bmax, grid_flat):
+    """lin [n] int64 (ids on the level lattice) -> (world points [n,3], interpolated values [n]);
+    marks the points in `calculated` (final-grid bool mask).  bmin / bmax: python float triples."""
+    _need_cuda(lin, calculated, grid_flat)
+    n = lin.numel()
+    dev = lin.device
+    fD, fH, fW = calculated.shape
+    pts = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    interp = torch.empty((n,), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    lo = (C.c_float * 3)(*[float(v) for v in bmin])
+    hi = (C.c_float * 3)(*[float(v) for v in bmax])
+    with torch.cuda.device(dev):
+        check(lib.sr_seg3d_gather(_p(lin), n, int(level_hw[0]), int(level_hw[1]), int(stride_zyx[0]),
+                                  int(stride_zyx[1]), int(stride_zyx[2]), fD, fH, fW, lo, hi, _p(grid_flat),
+                                  _p(pts), _p(interp), _p(calculated), _stream()), "seg3d_gather")
+    return pts, interp
+
+
+def seg3d_scatter(lin, values, interp, balance, grid_flat):
+    """grid[lin] = values; returns (conflict mask [numel(grid)] bool, n_conflicts int32[1] on device)."""
+    _need_cuda(lin, values, interp, grid_flat)
+    dev = lin.device
+    conflict = torch.empty((grid_flat.numel(),), dtype=torch.bool, device=dev)
+    ncf = torch.empty((1,), dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        check(lib.sr_seg3d_scatter(_p(lin), lin.numel(), _p(values), _p(interp), float(balance), _p(grid_flat),
+                                   _p(conflict), conflict.numel(), _p(ncf), _stream()), "seg3d_scatter")
+    return conflict, ncf
 
 
 # ------------------------------------------------------------------------------------------------
