@@ -375,10 +375,25 @@ __device__ __forceinline__ long long vertex_id(const McLayout& L, int oi, int oj
   return (long long)id;
 }
 
+// Same id from the word records staged in shared memory by mc_emit_kernel: rec[(dx + 2 dy... row) * 2 + wsel]
+// = {fx, fy, fz, cta_v + vpre} of word (i + dx, j + dy, kw + wsel).
+__device__ __forceinline__ long long vertex_id_rec(const McLayout& L, const uint4* rec, int kw, int oi, int oj,
+                                                   int ok, int row, int dir) {
+  if (oi >= L.nx - 1 || oj >= L.ny - 1 || ok >= L.nz - 1) return -1;
+  const uint4 r = rec[row * 2 + ((ok >> 5) - kw)];
+  const int bit = ok & 31;
+  const uint32_t lt = (1u << bit) - 1u;
+  uint32_t id = r.w + __popc(r.x & lt) + __popc(r.y & lt) + __popc(r.z & lt);
+  if (dir >= 1) id += (r.x >> bit) & 1u;
+  if (dir == 2) id += (r.y >> bit) & 1u;
+  return (long long)id;
+}
+
 __global__ void __launch_bounds__(kThreads)
 mc_emit_kernel(const float* __restrict__ sdf, McLayout L, float iso, float xs, float ys, float zs,
                float x0, float y0, float z0, int i_offset, float* __restrict__ verts,
                long long vcap, long long* __restrict__ faces, long long fcap) {
+  __shared__ uint4 s_rec[kWarps][8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long word0 = (long long)blockIdx.x * kWordsPerCta + (long long)warp * kWordsPerWarp;
   const uint32_t cta_v = L.cta_v[blockIdx.x], cta_t = L.cta_t[blockIdx.x];
@@ -408,6 +423,21 @@ mc_emit_kernel(const float* __restrict__ sdf, McLayout L, float iso, float xs, f
     const int k = kw * 32 + lane;
     float v[8];
     const int idx = load_cube(sdf, L.nx, L.ny, L.nz, i, j, k, iso, v);
+    // records of the eight words the faces of this word can reference: rows (i,j) (i+1,j) (i,j+1)
+    // (i+1,j+1) at kw and kw+1, fetched once by lanes 0..7 instead of five loads per face corner
+    __syncwarp();
+    if (lane < 8) {
+      const int row = lane >> 1, ws = lane & 1;
+      const int oi = i + (row & 1), oj = j + (row >> 1);
+      uint4 r = make_uint4(0u, 0u, 0u, 0u);
+      if (oi < L.nx && oj < L.ny && kw + ws < L.nwz) {
+        const uint32_t w = ((uint32_t)oi * (uint32_t)L.ny + (uint32_t)oj) * (uint32_t)L.nwz + (uint32_t)(kw + ws);
+        r = make_uint4(__ldg(L.fx + w), __ldg(L.fy + w), __ldg(L.fz + w),
+                       __ldg(L.cta_v + (w / kWordsPerCta)) + __ldg(L.vpre + w));
+      }
+      s_rec[warp][lane] = r;
+    }
+    __syncwarp();
     // ---- vertices owned by this voxel, ordered (k, dir)
     const uint32_t bitm = 1u << lane, lt = bitm - 1u;
     if ((fx | fy | fz) & bitm) {
@@ -462,7 +492,7 @@ mc_emit_kernel(const float* __restrict__ sdf, McLayout L, float iso, float xs, f
         const int dy = (0xC44 >> e) & 1;
         const int dz = (0x0F0 >> e) & 1;
         const int dir = e >= 8 ? 2 : (e & 1);
-        const long long id = vertex_id(L, i + dx, j + dy, k + dz, dir);
+        const long long id = vertex_id_rec(L, s_rec[warp], kw, i + dx, j + dy, k + dz, dx + 2 * dy, dir);
         if (fid < fcap) faces[fid * 3 + (2 - c)] = id;
       }
     }

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+run() { name=$1; shift; echo "=== $name" ; timeout "$@" > gpurun_out/$name.log 2>&1; echo "exit $? ($name)"; tail -n 3 gpurun_out/$name.log; }
+run tests_trace 600 python -m pytest tests -m gpu -q -k "trace or optim or smoke" --maxfail=10 --timeout 300
+run trace_bench 300 python tools/trace_bench.py
+run bench 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline
+grep -h '"metric"' gpurun_out/bench.log > gpurun_out/bench_line.json
