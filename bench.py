@@ -230,11 +230,11 @@ def cpu_reference_sample(n_rays, threads, seed=0, with_mc=True):
         t0 = time.perf_counter()
         with torch.no_grad():
             grid, calc = O.seg3d_forward(lambda q: sdf_fn(q).view(-1), [-1.0] * 3, [1.0] * 3,
-                                         synth.MC_LADDER_129, 0.0)
-        spc, org = O.mc_world_params([-1.0] * 3, [1.0] * 3, (129, 129, 129))
+                                         synth.MC_LADDER_257, 0.0)
+        spc, org = O.mc_world_params([-1.0] * 3, [1.0] * 3, (257, 257, 257))
         c_api.marching_cubes(grid.permute(2, 1, 0).contiguous().numpy(), helpers.mc_tri_table(), 0.0, spc, org)
         t_mc = time.perf_counter() - t0
-        out.update({"mc_grid": 129, "mc_seconds": t_mc, "mc_voxels_per_sec": 129 ** 3 / t_mc,
+        out.update({"mc_grid": 257, "mc_seconds": t_mc, "mc_voxels_per_sec": 257 ** 3 / t_mc,
                     "mc_queried": int(calc.sum())})
     return out
 
@@ -426,10 +426,13 @@ def main():
         "e2e": {"value": total_rays / (e2e_t * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms": e2e_t},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "tc_layer_kernel<softplus,1> (tcgen05 split-BF16 GEMM layer 512x512 of the tracer, "
-                               "M = rays of the frame; ~300 such launches per trace)",
+        "roofline": {"kernel": "tc_layer_pair_kernel<softplus,1> (tcgen05 cta_group::2 split-BF16 GEMM layer 512x512 of "
+                               "the tracer, M = rays of the frame; ~300 such launches per trace)",
                      "bound": "tensor", "achieved": layer_tf, "peak": pk["tensor"], "unit": "TFLOP/s",
-                     "frac": layer_tf / pk["tensor"], "traffic": None,
+                     "frac": layer_tf / pk["tensor"],
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at M = 50 333 from the
+                     # ncu --set full capture in profiles/r01c_summary.md (algorithmic: 103 MB in + 103 MB out)
+                     "traffic": 159.3e6 if n_rays == 50333 else None,
                      "peak_source": pk["src"] + " bf16 cuBLAS burst", "ms_per_launch": layer_ms,
                      "mma_terms": 3, "tensor_pipe_frac": 3.0 * layer_tf / pk["tensor"],
                      "note": "achieved = algorithmic fp32 FLOPs of one layer launch (2*M*512*512, SURVEY 8d: 0.524 "
@@ -443,18 +446,21 @@ def main():
                                "note": "SURVEY 8d counts a traced ray as (1+3k) network evaluations (forward-mode "
                                        "tangents, what the reference's autograd costs); this implementation runs "
                                        "one forward + one reverse sweep per iteration (2k+1 evaluations)"}},
-        "roofline_mc": {"kernel": "mc_classify+mc_scan+mc_emit", "bound": "hbm",
+        "roofline_mc": {"kernel": "mc_sign+mc_classify+mc_scan+mc_emit", "bound": "hbm",
                         "achieved": mc_bytes / mc_s / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-                        "frac": mc_bytes / mc_s / 1e9 / pk["hbm"], "traffic": None, "ms": mc_s * 1e3,
+                        "frac": mc_bytes / mc_s / 1e9 / pk["hbm"],
+                        # ncu capture of the four kernels (profiles/r01c_summary.md); algorithmic = mc_bytes
+                        "traffic": 92.6e6 if GRID_N == 257 else None, "algorithmic_bytes": mc_bytes,
+                        "ms": mc_s * 1e3,
                         "peak_source": pk["src"]},
         "clocks": clk.summary(),
         "wall_s_timed_region": t_wall,
     }
     if not args.no_cpu_baseline and world == 1:
         threads = pick_threads()
-        cb = cpu_reference_sample(16384, threads, with_mc=True)
+        cb = cpu_reference_sample(None, threads, with_mc=True)
         line["cpu_baseline"] = {"value": cb["rays_per_sec"], "unit": "rays/s", "cores": threads, "kind": "port",
-                                "sample": "16384 rays of the same frame (trace times=10 + shading) and a 129^3 "
+                                "sample": "all rays of the same frame (trace times=10 + shading) and the same 257^3 "
                                           "coarse-to-fine grid + MC through oracle/ (torch fp32 CPU + C)",
                                 "mc_voxels_per_sec": cb.get("mc_voxels_per_sec"), "mc_grid": cb.get("mc_grid"),
                                 "ray_seconds": cb["ray_seconds"], "mc_seconds": cb.get("mc_seconds")}
