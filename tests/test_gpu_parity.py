@@ -20,6 +20,11 @@ pytestmark = pytest.mark.gpu
 FP_TOL = 1e-4
 
 
+def helpers_root():
+    import helpers
+    return helpers.ROOT
+
+
 def _ref(name):
     from oracle import build
     return build.load_ref(name)
@@ -121,6 +126,15 @@ def test_mc_exact_vs_oracle(cuda_dev):
         assert v.dtype == torch.float32 and f.dtype == torch.int64
         assert np.array_equal(f.cpu().numpy(), fo), "face indices (canonical order) must be identical"
         assert np.array_equal(v.cpu().numpy(), vo), "vertex positions are bit-exact (double division + fmaf)"
+    # word-boundary shapes of the sign bit-plane (nz = 2, 32, 33, 64, 65, 97) on dense random-sign grids:
+    # every cell is active, every edge flag and every k -> k+1 word crossing is exercised
+    g = torch.Generator().manual_seed(99)
+    for shape in ((2, 2, 2), (3, 2, 33), (2, 5, 32), (4, 3, 64), (3, 4, 65), (5, 5, 97), (9, 7, 31)):
+        grid = (torch.rand(shape, generator=g) - 0.5).contiguous()
+        v, f = MCGpu.mc_gpu(grid.to(cuda_dev), 1, 1, 1, 0, 0, 0, 0.0)
+        vo, fo = c_api.marching_cubes(grid.numpy(), tt)
+        assert np.array_equal(f.cpu().numpy(), fo), shape
+        assert np.array_equal(v.cpu().numpy(), vo), shape
     # surface touching the +x/+y/+z boundary layer -> -1 indices exactly where the oracle has them
     grid = _test_grid(17, 5)
     grid[-1] = -1.0
@@ -460,6 +474,64 @@ def test_trace_vs_golden(cuda_dev):
                                       lambda q: O.sdf_forward(sp, q, 6, 1.0)[0], lambda q, b: q, 5e-5, 0.05,
                                       3.05, 1.0, 10)
     assert np.abs(res["reverse_id"].cpu().numpy() - po.numpy()).max() < 7e-5
+
+
+def test_seg3d_gather_scatter_match_the_torch_sequence(cuda_dev):
+    """lattice -> world arithmetic of batch_eval (seg3d_lossless.py:99-101): identical bits to the
+    torch op sequence; scatter: write-back, conflict mask and count."""
+    from selfreconcode_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    D, H, W = 17, 21, 15
+    fD, fH, fW = 65, 81, 57
+    sz, sy, sx = 4, 4, 4
+    bmin, bmax = [-0.9, -1.3, -0.5], [0.9, 0.95, 0.52]
+    lin = torch.randperm(D * H * W, generator=g)[:2000].sort()[0].to(cuda_dev)
+    grid = torch.randn(D * H * W, generator=g).to(cuda_dev)
+    calc = torch.zeros((fD, fH, fW), dtype=torch.bool, device=cuda_dev)
+    pts, interp = ops.seg3d_gather(lin, (H, W), (sz, sy, sx), calc, bmin, bmax, grid)
+    z, y, x = lin // (H * W), (lin // W) % H, lin % W
+    coords = torch.stack([x * sx, y * sy, z * sz], dim=1)
+    res = torch.tensor([fW, fH, fD], device=cuda_dev)
+    step = 1.0 / res.float()
+    c2 = coords.float() / res + step / 2
+    lo, hi = torch.tensor(bmin, device=cuda_dev), torch.tensor(bmax, device=cuda_dev)
+    want = c2 * (hi - lo) + lo
+    assert torch.equal(pts, want)
+    assert torch.equal(interp, grid[lin])
+    ref_calc = torch.zeros_like(calc)
+    ref_calc[coords[:, 2], coords[:, 1], coords[:, 0]] = True
+    assert torch.equal(calc, ref_calc)
+    vals = torch.randn(lin.numel(), generator=g).to(cuda_dev)
+    before = grid.clone()
+    conflict, ncf = ops.seg3d_scatter(lin, vals, interp, 0.05, grid)
+    want_c = (interp - 0.05) * (vals - 0.05) < 0
+    assert int(ncf.item()) == int(want_c.sum())
+    ref_mask = torch.zeros(D * H * W, dtype=torch.bool, device=cuda_dev)
+    ref_mask[lin[want_c]] = True
+    assert torch.equal(conflict, ref_mask)
+    before[lin] = vals
+    assert torch.equal(grid, before)
+
+
+def test_tc_pair_kernel_matches_single_cta_kernel(cuda_dev, monkeypatch):
+    """cta_group::2 kernel vs the single-CTA kernel: same operands, same MMA terms and order."""
+    import subprocess, sys, os, json
+    code = (
+        "import torch, json, sys; sys.path.insert(0, %r); from selfreconcode_b200 import ops; "
+        "from selfreconcode_b200._lib import SR_ACT_SOFTPLUS100; torch.manual_seed(0); "
+        "M=777; x=torch.randn(M,512,device='cuda'); w=torch.randn(512,512,device='cuda')/22.6; "
+        "b=torch.randn(512,device='cuda')*0.01; A=ops.tc_pack_rows(x); W=ops.tc_pack_weights(w); "
+        "o=ops.tc_linear(A,W,b,M,512,512,512,SR_ACT_SOFTPLUS100,want_out=True)[1]; "
+        "print(json.dumps(dict(s=float(o.double().sum()), a=float(o.double().abs().sum()), m=float(o.max()))))"
+    ) % helpers_root()
+    outs = []
+    for pair in ("1", "0"):
+        env = dict(os.environ, SELFRECON_B200_TC_PAIR=pair)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=240)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    for k in outs[0]:
+        assert abs(outs[0][k] - outs[1][k]) <= 1e-6 * abs(outs[1][k]), outs
 
 
 def test_seg3d_lossless_vs_golden_and_mc(cuda_dev):
