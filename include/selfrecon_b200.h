@@ -255,13 +255,16 @@ int sr_shade_geometry(const sr_mlp_desc* sdf, const sr_mlp_desc* dnet, const sr_
                       float* feat, int nfeat, float* dpos, uint8_t* inv_ok, cudaStream_t s);
 
 /* ------------------------------------------------------------------------------------------
- * Tensor-core engine for the dense layers (tcgen05 + TMEM + TMA bulk copies): fp32-faithful
- * BF16x3 split GEMM, one launch per layer,  C = act(A * W^T + b)  with the epilogue (bias,
- * activation, forward-mode tangent scaling, skip concat, re-split) fused.  Operands are kept in
+ * Tensor-core engine for the dense layers (tcgen05 + TMEM + TMA bulk copies): split-BF16 GEMM
+ * (x = b1 + b2, three bf16 MMAs per product, fp32 accumulation in TMEM; measured error of the
+ * 8x512 SDF vs fp64: 2.4e-5 abs), one launch per layer,  C = act(A * W^T + b)  with the epilogue
+ * (bias, activation, forward-mode tangent scaling, skip concat, re-split) fused; layers whose
+ * width is a multiple of 256 run on CTA pairs (cta_group::2).  Operands are kept in
  * global memory in the UMMA canonical tile layout (see csrc/tc_gemm.cu):
  *   sr_tc_act_bytes(M,K) / sr_tc_weight_bytes(N,K): buffer sizes of tiled activations / weights
- *   sr_tc_pack_rows    : fp32 row-major [M][K] (ld) -> tiled bf16x3 activations
- *   sr_tc_pack_weights : fp32 row-major [N][K] (ld) effective weights -> tiled bf16x3
+ *   sr_tc_pack_rows    : fp32 row-major [M][K] (ld) -> tiled split-bf16 activations
+ *   sr_tc_pack_weights : fp32 row-major [N][K] (ld) effective weights -> tiled split-bf16
+ *                        (the single-CTA layout followed by the CTA-pair layout)
  *   sr_tc_linear       : one layer. A (tiled, K), W (tiled, N x K), bias [pad256(N)];
  *                        n_valid output columns; ch = rows per point (1, or 4 = value + 3
  *                        tangents: tangent rows get act'(z_value) * acc, no bias);

@@ -232,7 +232,7 @@ struct EpiRow {
 
 // One 32-column chunk of the accumulator (this thread: one row): bias / activation / tangent
 // scaling (forward) or act' multiply (reverse), then the fp32 outputs, the act' stash and the
-// re-split bf16x3 tile of the next layer.  `live` = the chunk holds GEMM columns (else only the
+// re-split bf16 tile of the next layer.  `live` = the chunk holds GEMM columns (else only the
 // zero padding / skip-connection columns of the next layer's input are produced).
 template <int ACT, int CH, bool MUL>
 __device__ __forceinline__ void epi_chunk(const LayerArgs& a, const EpiRow& r, uint32_t (&v)[32], int chunk,
@@ -770,7 +770,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 }
 
 // ---- packing kernels -------------------------------------------------------------------------
-// fp32 row-major [M][K] (ld) -> tiled bf16x3 activations with KC = ceil(Kpad/32) chunks
+// fp32 row-major [M][K] (ld) -> tiled split-bf16 activations with KC = ceil(Kpad/32) chunks
 __global__ void pack_rows_kernel(const float* __restrict__ src, long long M, int K, int ld,
                                  __nv_bfloat16* __restrict__ dst, int KC, long long MT,
                                  const int* __restrict__ m_dev) {
@@ -803,7 +803,7 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, long long M, int
   }
 }
 
-// effective weights, fp32 row-major [N][K] (ld) -> tiled bf16x3 [NT][KC][3][256x32]
+// effective weights, fp32 row-major [N][K] (ld) -> tiled split-bf16 [NT][KC][planes][256x32] followed by the CTA-pair layout
 __global__ void pack_weights_kernel(const float* __restrict__ w, int N, int K, int ld,
                                     __nv_bfloat16* __restrict__ dst, int NT, int KC) {
   const long long total = (long long)NT * BN * KC * 4;

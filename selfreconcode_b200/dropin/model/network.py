@@ -107,7 +107,7 @@ class ImplicitNetwork(nn.Module):
         pts = input.detach().reshape(-1, 3)
         if ops.TC_ENABLED and not want_grad and nfeat == 0 and pts.shape[0] >= ops.TC_MIN_POINTS:
             # large value-only batches (the 257^3 / 513^3 grid queries): tensor-core engine
-            # (tcgen05 BF16x3 split GEMM per layer, csrc/tc_gemm.cu)
+            # (tcgen05 split-BF16 GEMM per layer, csrc/tc_gemm.cu)
             sdf = ops.tc_mlp_forward(net, pts, ch=1, n_out=1)
             return sdf.view(-1, 1), None, None
         sdf, grad, feat = ops.sdf_forward(net, pts, want_grad, nfeat)

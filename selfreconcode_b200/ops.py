@@ -17,7 +17,7 @@ from ._lib import check as _check
 
 import os as _os
 
-# Tensor-core engine switch: large batches go to the tcgen05 BF16x3 layer GEMMs, small ones to the
+# Tensor-core engine switch: large batches go to the tcgen05 split-BF16 layer GEMMs, small ones to the
 # fused fp32 FFMA engine (one persistent kernel, lower latency).  SELFRECON_B200_TC=0 disables it.
 TC_ENABLED = _os.environ.get("SELFRECON_B200_TC", "1") != "0"
 TC_MIN_POINTS = int(_os.environ.get("SELFRECON_B200_TC_MIN_POINTS", "16384"))
@@ -451,7 +451,7 @@ def trace_surface_points(sdf_net, def_net, lbs, cam_pos, rays, init_pts, batch_i
                          dthreshold=5e-5, athreshold=0.02, w1=3.05, w2=1.0, times=5,
                          return_counters=False, mode="auto"):
     """OptimizeSurfacePs (utils/FindSurfacePs.py:114-163): returns (points, converged).
-    Nothing syncs the host.  mode: "tc" = dense layers on the tensor-core engine (tcgen05 BF16x3,
+    Nothing syncs the host.  mode: "tc" = dense layers on the tensor-core engine (tcgen05 split-BF16,
     reverse-mode sweeps), "reverse" / "forward" = fused fp32 FFMA engine (times+1 launches of one
     persistent kernel), "auto" = "tc" for large ray sets, "reverse" otherwise."""
     if mode == "auto":
@@ -577,10 +577,10 @@ def seg3d_scatter(lin, values, interp, balance, grid_flat):
 
 
 # ------------------------------------------------------------------------------------------------
-# Tensor-core (tcgen05, BF16x3) layer engine
+# Tensor-core (tcgen05, split-BF16) layer engine
 # ------------------------------------------------------------------------------------------------
 def tc_pack_rows(x):
-    """fp32 [M,K] -> tiled bf16x3 activation buffer (uint8 tensor)."""
+    """fp32 [M,K] -> tiled split-bf16 activation buffer (uint8 tensor)."""
     _need_cuda(x)
     x = x.contiguous().float()
     M, K = x.shape
@@ -592,7 +592,7 @@ def tc_pack_rows(x):
 
 
 def tc_pack_weights(w):
-    """effective weights fp32 [N,K] -> tiled bf16x3 weight buffer (uint8 tensor)."""
+    """effective weights fp32 [N,K] -> tiled split-bf16 weight buffer (single-CTA + CTA-pair layouts) (uint8 tensor)."""
     _need_cuda(w)
     w = w.contiguous().float()
     N, K = w.shape
@@ -624,7 +624,7 @@ def tc_linear(A, W, bias, M, N, K, n_valid, act, ch=1, K_next=0, scale=1.0, skip
 
 
 class TcNet:
-    """Tensor-core view of a FusedMLP: the same folded weights packed as tiled bf16x3 operands.
+    """Tensor-core view of a FusedMLP: the same folded weights packed as tiled split-bf16 operands.
     Built lazily from the FusedMLP's un-transposed padded copies (`wb`), cached on the FusedMLP."""
 
     def __init__(self, fused):

@@ -569,9 +569,9 @@ def test_seg3d_lossless_vs_golden_and_mc(cuda_dev):
 
 
 # ------------------------------------------------------------------------------------------------
-# Tensor-core engine (tcgen05, BF16x3 split) -- fp32-faithful GEMM layers
+# Tensor-core engine (tcgen05, split-BF16 operands, fp32 accumulation in TMEM)
 # ------------------------------------------------------------------------------------------------
-def test_tc_linear_bf16x3_matches_fp64(cuda_dev):
+def test_tc_linear_split_bf16_matches_fp64(cuda_dev):
     from selfreconcode_b200 import ops
     from selfreconcode_b200._lib import SR_ACT_NONE, SR_ACT_SOFTPLUS100, SR_ACT_RELU
     g = torch.Generator().manual_seed(7)
