@@ -20,59 +20,67 @@ constexpr int kThreads = 256;
 //   odd {y,z} (x even): (z-,y-),(z+,y-),(z-,y+),(z+,y+)            -> z fastest
 //   odd {x,z} (y even): (z-,x-),(z+,x-),(z-,x+),(z+,x+)            -> z fastest
 //   odd {x,y,z}        : x fastest, then y, then z
+// One CTA per output row (b, z, y): the parities of y and z -- and with them the tap pattern -- are
+// uniform in the CTA, and thread t produces the output pair x = 2t (even) and x = 2t+1 (odd) from the
+// source columns t and t+1 of the (up to four) source rows, so there is no per-voxel div/mod and no
+// divergent switch (the first version had both and ran at 0.4 TB/s).
 __global__ void __launch_bounds__(kThreads)
 interp2x3d_fwd_kernel(const float* __restrict__ in, float* __restrict__ out,
                       uint8_t* __restrict__ bnd, int bc, int d, int h, int w, float balance) {
   const int od = 2 * d - 1, oh = 2 * h - 1, ow = 2 * w - 1;
-  const long long per = (long long)od * oh * ow;
-  const long long total = per * bc;
-  for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * kThreads) {
-    const int x = (int)(idx % ow);
-    const int y = (int)((idx / ow) % oh);
-    const int z = (int)((idx / ((long long)ow * oh)) % od);
-    const long long b = idx / per;
-    const float* src = in + b * (long long)d * h * w;
-    const int ox = x & 1, oy = y & 1, oz = z & 1;
-    const int x0 = (x - ox) >> 1, x1 = (x + ox) >> 1;
-    const int y0 = (y - oy) >> 1, y1 = (y + oy) >> 1;
-    const int z0 = (z - oz) >> 1, z1 = (z + oz) >> 1;
-#define AT(zz, yy, xx) __ldg(src + ((long long)(zz) * h + (yy)) * w + (xx))
-    float v[8];
-    int n = 1;
-    const int code = ox | (oy << 1) | (oz << 2);
-    switch (code) {
-      case 0: v[0] = AT(z0, y0, x0); n = 1; break;
-      case 1: v[0] = AT(z0, y0, x0); v[1] = AT(z0, y0, x1); n = 2; break;
-      case 2: v[0] = AT(z0, y0, x0); v[1] = AT(z0, y1, x0); n = 2; break;
-      case 4: v[0] = AT(z0, y0, x0); v[1] = AT(z1, y0, x0); n = 2; break;
-      case 3:  // x,y odd
-        v[0] = AT(z0, y0, x0); v[1] = AT(z0, y0, x1); v[2] = AT(z0, y1, x0); v[3] = AT(z0, y1, x1);
-        n = 4; break;
-      case 6:  // y,z odd (x even): z fastest
-        v[0] = AT(z0, y0, x0); v[1] = AT(z1, y0, x0); v[2] = AT(z0, y1, x0); v[3] = AT(z1, y1, x0);
-        n = 4; break;
-      case 5:  // x,z odd (y even): z fastest
-        v[0] = AT(z0, y0, x0); v[1] = AT(z1, y0, x0); v[2] = AT(z0, y0, x1); v[3] = AT(z1, y0, x1);
-        n = 4; break;
-      default:  // 7
-        v[0] = AT(z0, y0, x0); v[1] = AT(z0, y0, x1); v[2] = AT(z0, y1, x0); v[3] = AT(z0, y1, x1);
-        v[4] = AT(z1, y0, x0); v[5] = AT(z1, y0, x1); v[6] = AT(z1, y1, x0); v[7] = AT(z1, y1, x1);
-        n = 8; break;
+  const long long rows = (long long)bc * od * oh;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int y = (int)(row % oh);
+    const int z = (int)((row / oh) % od);
+    const long long b = row / ((long long)oh * od);
+    const int oy = y & 1, oz = z & 1;
+    const int y0 = (y - oy) >> 1, y1 = (y + oy) >> 1, z0 = (z - oz) >> 1, z1 = (z + oz) >> 1;
+    const float* s00 = in + ((b * d + z0) * (long long)h + y0) * w;   // (z0, y0)
+    const float* s01 = in + ((b * d + z0) * (long long)h + y1) * w;   // (z0, y1)
+    const float* s10 = in + ((b * d + z1) * (long long)h + y0) * w;   // (z1, y0)
+    const float* s11 = in + ((b * d + z1) * (long long)h + y1) * w;   // (z1, y1)
+    float* orow = out + row * ow;
+    uint8_t* brow = bnd + row * ow;
+    for (int t = threadIdx.x; t < w; t += kThreads) {
+      const bool has_odd = t + 1 < w;
+      const int t1 = has_odd ? t + 1 : t;
+      // a[z][y][x]
+      const float a000 = __ldg(s00 + t), a001 = __ldg(s00 + t1);
+      const float a010 = oy ? __ldg(s01 + t) : a000, a011 = oy ? __ldg(s01 + t1) : a001;
+      const float a100 = oz ? __ldg(s10 + t) : a000, a101 = oz ? __ldg(s10 + t1) : a001;
+      const float a110 = (oy & oz) ? __ldg(s11 + t) : (oz ? a100 : a010);
+      const float a111 = (oy & oz) ? __ldg(s11 + t1) : (oz ? a101 : a011);
+      float ve, vo;      // even-x and odd-x outputs
+      bool de, dodd;     // their boundary flags
+      const bool f0 = a000 > balance;
+      // sums in the reference's tap order (see the table above); /2 /4 /8 are exact
+      if (!oy && !oz) {
+        ve = a000; de = false;
+        vo = __fadd_rn(a000, a001) * 0.5f; dodd = (a001 > balance) != f0;
+      } else if (oy && !oz) {
+        ve = __fadd_rn(a000, a010) * 0.5f; de = (a010 > balance) != f0;
+        vo = __fadd_rn(__fadd_rn(__fadd_rn(a000, a001), a010), a011) * 0.25f;
+        dodd = ((a001 > balance) != f0) | ((a010 > balance) != f0) | ((a011 > balance) != f0);
+      } else if (!oy && oz) {
+        ve = __fadd_rn(a000, a100) * 0.5f; de = (a100 > balance) != f0;
+        vo = __fadd_rn(__fadd_rn(__fadd_rn(a000, a100), a001), a101) * 0.25f;     // z fastest
+        dodd = ((a100 > balance) != f0) | ((a001 > balance) != f0) | ((a101 > balance) != f0);
+      } else {
+        ve = __fadd_rn(__fadd_rn(__fadd_rn(a000, a100), a010), a110) * 0.25f;     // z fastest
+        de = ((a100 > balance) != f0) | ((a010 > balance) != f0) | ((a110 > balance) != f0);
+        vo = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(a000, a001), a010), a011), a100),
+                                           a101), a110), a111) * 0.125f;           // x, then y, then z
+        dodd = ((a001 > balance) != f0) | ((a010 > balance) != f0) | ((a011 > balance) != f0) |
+               ((a100 > balance) != f0) | ((a101 > balance) != f0) | ((a110 > balance) != f0) |
+               ((a111 > balance) != f0);
+      }
+      orow[2 * t] = ve;
+      brow[2 * t] = de ? 1 : 0;
+      if (has_odd) {
+        orow[2 * t + 1] = vo;
+        brow[2 * t + 1] = dodd ? 1 : 0;
+      }
     }
-#undef AT
-    float sum = v[0];
-    const bool f0 = v[0] > balance;
-    bool differ = false;
-    for (int t = 1; t < n; ++t) {
-      sum = __fadd_rn(sum, v[t]);
-      differ |= ((v[t] > balance) != f0);
-    }
-    // division by 2/4/8 is exact in binary floating point (the reference divides by the
-    // double literals 2., 4.0, 8.0 and rounds back: same value).
-    const float scale = n == 1 ? 1.0f : (n == 2 ? 0.5f : (n == 4 ? 0.25f : 0.125f));
-    out[idx] = sum * scale;
-    bnd[idx] = differ ? 1 : 0;
   }
 }
 
