@@ -361,21 +361,9 @@ __device__ __forceinline__ float edge_offset(float v1, float v2, float iso) {
   return (float)((double)__fsub_rn(iso, v1) / delta);
 }
 
-// vertex id of the edge (dir) owned by voxel (oi,oj,ok); -1 when that voxel is not a cell.
-__device__ __forceinline__ long long vertex_id(const McLayout& L, int oi, int oj, int ok, int dir) {
-  if (oi >= L.nx - 1 || oj >= L.ny - 1 || ok >= L.nz - 1) return -1;
-  const uint32_t word = ((uint32_t)oi * (uint32_t)L.ny + (uint32_t)oj) * (uint32_t)L.nwz + (uint32_t)(ok >> 5);
-  const int bit = ok & 31;
-  const uint32_t lt = (1u << bit) - 1u;
-  const uint32_t fx = __ldg(L.fx + word), fy = __ldg(L.fy + word), fz = __ldg(L.fz + word);
-  uint32_t id = __ldg(L.cta_v + (word / kWordsPerCta)) + __ldg(L.vpre + word) + __popc(fx & lt) +
-                __popc(fy & lt) + __popc(fz & lt);
-  if (dir >= 1) id += (fx >> bit) & 1u;
-  if (dir == 2) id += (fy >> bit) & 1u;
-  return (long long)id;
-}
-
-// Same id from the word records staged in shared memory by mc_emit_kernel: rec[(dx + 2 dy... row) * 2 + wsel]
+// vertex id of the edge (dir) owned by voxel (oi,oj,ok), -1 when that voxel is not a cell:
+//   id = cta_v[word / 256] + vpre[word] + popc(fx, fy, fz below bit k) (+ fx, fy of bit k for dir y, z),
+// evaluated from the word records staged in shared memory by mc_emit_kernel: rec[(dx + 2 dy) * 2 + wsel]
 // = {fx, fy, fz, cta_v + vpre} of word (i + dx, j + dy, kw + wsel).
 __device__ __forceinline__ long long vertex_id_rec(const McLayout& L, const uint4* rec, int kw, int oi, int oj,
                                                    int ok, int row, int dir) {

@@ -836,7 +836,7 @@ def _tc_trace_body(lib, G, sdf_net, def_net, ts, td, tp, P, times, condlen, has_
         idx = lists[(it + 1) & 1] if it > 0 else None
         a_out = lists[it & 1] if it < times else None
         m_dev = counters[it:it + 1]
-        # ---- forward sweeps (act' stashed when an update follows)
+        # ---- forward sweeps (each layer keeps its output tiles for the reverse sweep)
         check(lib.sr_tc_embed(_p(pts), P, ds.multires, pw_s, 1, None, None, 0, 0, _p(B.emb_s), B.ld_s,
                               _p(idx), _p(m_dev), _stream()), "tc_embed")
         _tc_forward_sweep(lib, sdf_net, ts, B.emb_s, B.ld_s, B.A_in, B.acts_s, P, m_dev, B.f)
