@@ -247,7 +247,8 @@ def main():
     row = pix[:, 1].round().long()
     tmpps = pstar[:Pg] + 2e-3 * torch.randn(Pg, 3, generator=g)
     gl = torch.randn(Pg, 3, generator=g)
-    out = dict(col=col.numpy(), row=row.numpy(), batch_inds=bi2[:Pg].numpy(), tmpps=tmpps.numpy(),
+    out = dict(cam_project_in=dg.numpy(), cam_project=pix.numpy(), cam_pos=cam0.cam_pos().numpy(),
+               col=col.numpy(), row=row.numpy(), batch_inds=bi2[:Pg].numpy(), tmpps=tmpps.numpy(),
                grad_l_p=gl.numpy(), focals=focals0.numpy(), pps=pps0.numpy(), Rs=Rs0.numpy(), Ts=Ts0.numpy(),
                H=Hh, W=Ww, angthr=cam0.angThreshold(0.5))
     for case in ("fixedcam", "optcam"):

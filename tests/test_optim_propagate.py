@@ -110,6 +110,21 @@ def run_case(case, device):
     assert seen >= 20 + (4 if opt else 0)
 
 
+def test_camera_matches_the_reference_class():
+    """RectifiedPerspectiveCameras.project / cam_pos / view_rays / angThreshold (model/CameraMine.py:129-170)
+    against values produced by the reference's own methods (oracle/make_golden.py)."""
+    H.dropin()
+    from model.CameraMine import RectifiedPerspectiveCameras
+    g = H.golden("propagate.npz")
+    t = lambda k: torch.from_numpy(g[k])
+    cam = RectifiedPerspectiveCameras(t("focals"), t("pps"), t("Rs"), t("Ts"), image_size=[(int(g["W"]), int(g["H"]))])
+    np.testing.assert_allclose(cam.project(t("cam_project_in")).numpy(), g["cam_project"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(cam.cam_pos().numpy(), g["cam_pos"], rtol=0, atol=1e-7)
+    assert abs(cam.angThreshold(0.5) - float(g["angthr"])) < 1e-7
+    pix = torch.stack([t("col"), t("row"), torch.ones_like(t("col"))], dim=1).float()
+    np.testing.assert_allclose(cam.view_rays(pix).numpy(), g["fixedcam_rays"], rtol=0, atol=2e-6)
+
+
 @pytest.mark.parametrize("case", ["fixedcam", "optcam"])
 def test_propagate_host_logic_cpu(case, monkeypatch):
     H.dropin()
