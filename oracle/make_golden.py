@@ -333,6 +333,28 @@ def main():
     np.savez_compressed(os.path.join(OUT, "seg3d_aniso.npz"), **pack_grid(grid2[0, 0], queried2),
                         ladder=np.array(ladder2))
 
+    # ---------------------------------------------------------------- small helpers (a9, a18)
+    from utils.FindSurfacePs import FindSurfacePs as ref_find
+    g = torch.Generator().manual_seed(81)
+    Nf, Hf, Wf, Kf, nF, nV = 2, 12, 10, 3, 40, 30
+    p2f = torch.randint(-1, 2 * nF, (Nf, Hf, Wf, Kf), generator=g)        # packed face ids of 2 meshes, -1 = miss
+    bary = torch.rand(Nf, Hf, Wf, Kf, 3, generator=g) - 0.15              # some non-positive weights
+    TmpVs = torch.randn(nV, 3, generator=g)
+    TmpFs = torch.randint(0, nV, (nF, 3), generator=g)
+    frags = types.SimpleNamespace(pix_to_face=p2f, bary_coords=bary)
+    bi_, ri_, ci_, ps_, finds_ = ref_find(TmpVs, TmpFs, frags)
+    torch.manual_seed(82)
+    pc = torch.randn(60, 3)
+    sp = utils.sample_points(pc, 1.8, 0.01)
+    xg = torch.linspace(0.0, 3.0, 25)
+    qs = torch.randn(9, 4, generator=g)
+    np.savez(os.path.join(OUT, "utils_misc.npz"), p2f=p2f.numpy(), bary=bary.numpy(), TmpVs=TmpVs.numpy(),
+             TmpFs=TmpFs.numpy(), f_batch=bi_.numpy(), f_row=ri_.numpy(), f_col=ci_.numpy(), f_ps=ps_.numpy(),
+             f_finds=finds_.numpy(), pc=pc.numpy(), sample=sp.numpy(), gm_x=xg.numpy(),
+             gm=utils.GMRobustError(xg, 0.5).numpy(), gm_sq=utils.GMRobustError(xg, 0.5, True).numpy(),
+             quat=qs.numpy(), quat_R=utils.quat2mat(qs).numpy(), apose0=utils.smpl_tmp_Apose(0),
+             apose1=utils.smpl_tmp_Apose(1))
+
     # ---------------------------------------------------------------- batch_rodrigues
     g = torch.Generator().manual_seed(61)
     th = torch.randn(40, 3, generator=g)
