@@ -186,6 +186,11 @@ def main():
     np.savez(os.path.join(OUT, "render.npz"), seed=2, checksum=checksum(rn), pts=rp.numpy(),
              normals=rn_.numpy(), views=rv.numpy(), feat=rf.numpy(), rgb=col.detach().numpy())
 
+    # deformed normals through the reference helper (utils/utils.py:132-153), full-size SDF + composite deformer
+    p = pts.clone().requires_grad_(True)
+    dn, dds = utils.compute_deformed_normals(sdf_full, comp, p, [dcond, [poses, trans]], bi, RATIO, 'test')
+    np.savez(os.path.join(OUT, "normals.npz"), normals=dn.detach().numpy(), ds=dds.detach().numpy())
+
     # ---------------------------------------------------------------- OptimizeSurfacePs
     # full-size sdf + composite deformer from above, a handful of rays aimed through D(p*)
     g = torch.Generator().manual_seed(51)

@@ -425,6 +425,24 @@ def test_cardinal_rays_and_shade_geometry(cuda_dev):
     assert ok.all()
 
 
+def test_deformed_normals_vs_golden(cuda_dev):
+    """utils.compute_deformed_normals (utils/utils.py:132-153) on the fused kernels vs the reference's values."""
+    g, n, gs = golden("deform.npz"), golden("normals.npz"), golden("sdf_full.npz")
+    comp, conds = _deform_modules(g, cuda_dev)
+    sdf = build_sdf_full(gs).to(cuda_dev)
+    pts = torch.from_numpy(g["pts"]).to(cuda_dev)
+    bi = torch.from_numpy(g["batch_inds"]).to(cuda_dev)
+    dropin()
+    import utils
+    nx, ds = utils.compute_deformed_normals(sdf, comp, pts, conds, bi, RATIO, 'test')
+    assert rel_err(nx.cpu().numpy(), n["normals"]) < FP_TOL
+    assert rel_err(ds.cpu().numpy(), n["ds"]) < FP_TOL
+    # the autograd ('train') phase goes through the same math
+    p = pts.clone().requires_grad_(True)
+    nx2, _ = utils.compute_deformed_normals(sdf, comp, p, conds, bi, RATIO, 'train')
+    assert rel_err(nx2.detach().cpu().numpy(), n["normals"]) < FP_TOL
+
+
 def test_trace_vs_golden(cuda_dev):
     t, g, gs = golden("trace.npz"), golden("deform.npz"), golden("sdf_full.npz")
     comp, conds = _deform_modules(g, cuda_dev)

@@ -81,6 +81,19 @@ def test_cardinal_rays():
     assert rel_err(ds.numpy(), c["ds"]) < TOL
 
 
+def test_deformed_normals():
+    g, n, gs = golden("deform.npz"), golden("normals.npz"), golden("sdf_full.npz")
+    tr, lbs, _ = _deform_setup(g)
+    sdf = build_sdf_full(gs)
+    pts, bi = torch.from_numpy(g["pts"]), torch.from_numpy(g["batch_inds"])
+    dcond = torch.from_numpy(g["dcond"])
+    fn = lambda p: O.composite_deform(plain_params(tr), 6, float(g["def_ratio"]), dcond, lbs, p, bi)[0]
+    sfn = lambda p: O.sdf_forward(sdf_params(sdf), p, 6, 1.0)[0]
+    nn, ds = O.deformed_normals(sfn, fn, pts)
+    assert rel_err(nn.numpy(), n["normals"]) < 50 * TOL
+    assert rel_err(ds.numpy(), n["ds"]) < TOL
+
+
 def test_render_net():
     g = golden("render.npz")
     rn = build_render(g)
