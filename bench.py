@@ -155,25 +155,34 @@ def mc_part(sc, eng):
 
 def layer_roofline(dev, M, launches=24):
     """Live timing of the dominant kernel: one 512x512 softplus layer of the tracer on M rows
-    (tc_layer_kernel), CUDA events on the launching stream, rotating operand buffers so that no
-    launch finds its rows in L2 (4 x (in + out) > 126 MB)."""
-    from selfreconcode_b200 import ops
+    (tc_layer_pair_kernel), CUDA events on the launching stream, rotating operand buffers so that no
+    launch finds its rows in L2 (4 x (in + out) > 126 MB).  Bias and outputs are allocated once: the
+    timed region holds nothing but the layer launches."""
+    import ctypes as C
+    from selfreconcode_b200 import ops, _lib
     from selfreconcode_b200._lib import SR_ACT_SOFTPLUS100
+    lib = _lib.load()
     g = torch.Generator(device=dev).manual_seed(3)
     w = torch.randn(512, 512, device=dev, generator=g) / 22.6
     b = torch.zeros(512, device=dev)
     W = ops.tc_pack_weights(w)
     As = [ops.tc_pack_rows(torch.randn(M, 512, device=dev, generator=g)) for _ in range(4)]
+    outs = [torch.empty_like(As[0]) for _ in range(4)]
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    vp = lambda t: C.c_void_p(t.data_ptr())
+
+    def launch(i):
+        rc = lib.sr_tc_linear(vp(As[i & 3]), vp(W), vp(b), M, 512, 512, 512, SR_ACT_SOFTPLUS100, 1, vp(outs[i & 3]),
+                              512, 1.0, None, 0, 0, None, 0, 0, 512, None, None, 0, 0, 1.0, None, st)
+        assert rc == 0, rc
+
     for i in range(4):
-        ops.tc_linear(As[i], W, b, M, 512, 512, 512, SR_ACT_SOFTPLUS100, K_next=512)
+        launch(i)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    outs = []
     e0.record()
     for i in range(launches):
-        outs.append(ops.tc_linear(As[i & 3], W, b, M, 512, 512, 512, SR_ACT_SOFTPLUS100, K_next=512)[0])
-        if len(outs) > 4:
-            outs.pop(0)
+        launch(i)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / launches
@@ -192,8 +201,10 @@ def ray_part_api(sc, rays, init, bi):
 
 
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_sample(n_rays, threads, seed=0, with_mc=True):
-    """The oracle (CPU port of the reference path) on a bounded sample of the same workload."""
+def cpu_reference_sample(n_rays, threads, seed=0, with_mc=True, rays=None, keep=False):
+    """The oracle (CPU port of the reference path) on a bounded sample of the same workload.
+    `rays` = the GPU arm's own ray set (CPU tensors): same inputs, so `keep=True` results can be compared
+    element by element with the GPU's (parity_report)."""
     from selfreconcode_b200 import synth
     from oracle import oracle as O
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -212,19 +223,29 @@ def cpu_reference_sample(n_rays, threads, seed=0, with_mc=True):
     sdf_fn = lambda p: O.sdf_forward(sp, p, 6, 1.0)[0]
     def_fn = lambda p, b: O.composite_deform(tp, 6, 1.0, dcond, lbs, p, b)[0]
     cam = synth.camera(512, 512)
-    with torch.no_grad():
-        rays = synth.make_rays(cam, 1, lambda p: sdf_fn(p).view(-1), def_fn, seed=7 + seed, max_rays=n_rays)
+    if rays is None:
+        with torch.no_grad():
+            rays = synth.make_rays(cam, 1, lambda p: sdf_fn(p).view(-1), def_fn, seed=7 + seed, max_rays=n_rays)
+    elif n_rays is not None and n_rays < rays["rays"].shape[0]:
+        g = torch.Generator().manual_seed(11)
+        sel = torch.randperm(rays["rays"].shape[0], generator=g)[:n_rays].sort()[0]
+        rays = {k: v[sel] for k, v in rays.items() if torch.is_tensor(v) and v.shape[0] == rays["rays"].shape[0]}
     bi = rays["batch_inds"]
+    ang_thr = synth.ang_threshold(cam, 0.5)
     t0 = time.perf_counter()
     pts, conv, _ = O.optimize_surface_ps(cam["cam_pos"], rays["rays"], rays["init_pts"], bi, sdf_fn, def_fn,
-                                         5e-5, synth.ang_threshold(cam, 0.5), 3.05, 1.0, 10)
+                                         5e-5, ang_thr, 3.05, 1.0, 10)
     s, g, feat = O.sdf_value_and_grad(sp, pts, 6, 1.0)
     nx = g / g.norm(dim=1, keepdim=True)
     cr, ds, J, ok = O.cardinal_rays(lambda p: def_fn(p, bi), pts, rays["rays"])
     with torch.no_grad():
-        O.render_forward(rp, pts, nx, cr, feat, 4, 1.0)
+        rgb = O.render_forward(rp, pts, nx, cr, feat, 4, 1.0)
     t_ray = time.perf_counter() - t0
     out = {"rays": int(pts.shape[0]), "ray_seconds": t_ray, "rays_per_sec": pts.shape[0] / t_ray}
+    if keep:
+        u = ds - cam["cam_pos"].view(1, 3)
+        ang = torch.asin(torch.linalg.cross(u, rays["rays"]).norm(dim=1) / u.norm(dim=1)) * 180.0 / np.pi
+        out["keep"] = dict(pts=pts, conv=conv, rgb=rgb, f=s, ang=ang, ang_thr=ang_thr)
     if with_mc:
         from oracle import c_api
         t0 = time.perf_counter()
@@ -232,11 +253,54 @@ def cpu_reference_sample(n_rays, threads, seed=0, with_mc=True):
             grid, calc = O.seg3d_forward(lambda q: sdf_fn(q).view(-1), [-1.0] * 3, [1.0] * 3,
                                          synth.MC_LADDER_257, 0.0)
         spc, org = O.mc_world_params([-1.0] * 3, [1.0] * 3, (257, 257, 257))
-        c_api.marching_cubes(grid.permute(2, 1, 0).contiguous().numpy(), helpers.mc_tri_table(), 0.0, spc, org)
+        vo, fo = c_api.marching_cubes(grid.permute(2, 1, 0).contiguous().numpy(), helpers.mc_tri_table(), 0.0,
+                                      spc, org)
         t_mc = time.perf_counter() - t0
         out.update({"mc_grid": 257, "mc_seconds": t_mc, "mc_voxels_per_sec": 257 ** 3 / t_mc,
                     "mc_queried": int(calc.sum())})
+        if keep:
+            out["keep"].update(grid=grid, calc=calc, verts=vo, faces=fo)
     return out
+
+
+def parity_report(gpu, cpu, dthr=5e-5, f_band=1e-5, a_band=5e-4):
+    """GPU arm vs the oracle on the SAME inputs at the benchmark's own sizes (BASELINE config[1]):
+    counts only, printed in the JSON line and asserted by tests/test_gpu_baseline_parity.py.
+      points   : elementwise |a-b| <= 1e-4*|b| + 1e-4*mean|b|
+      mask     : convergence mismatches, and how many of them are NOT borderline in the oracle's own final
+                 state (| |f| - dthr | < f_band or | angle - athr | < a_band)
+      grid     : queried-voxel sets, sign pattern of the whole 257^3 grid, marching-cubes faces (bit-exact
+                 vertex indices) and vertex positions."""
+    rep = {}
+    pg, pc = gpu["pts"].double().cpu().numpy(), cpu["pts"].double().numpy()
+    tol = 1e-4 * np.abs(pc) + 1e-4 * np.abs(pc).mean()
+    rep["rays"] = int(pc.shape[0])
+    rep["pts_max_abs_err"] = float(np.abs(pg - pc).max())
+    rep["pts_elems_over_1e-4_rel"] = int((np.abs(pg - pc) > tol).sum())
+    cg, cc = gpu["conv"].cpu().numpy().astype(bool), cpu["conv"].numpy().astype(bool)
+    mm = cg != cc
+    f, ang = np.abs(cpu["f"].numpy()), cpu["ang"].numpy()
+    border = (np.abs(f - dthr) < f_band) | (np.abs(ang - cpu["ang_thr"]) < a_band)
+    rep["converged_gpu"], rep["converged_oracle"] = int(cg.sum()), int(cc.sum())
+    rep["conv_mismatch"] = int(mm.sum())
+    rep["conv_mismatch_not_borderline"] = int((mm & ~border).sum())
+    rg, rc = gpu["rgb"].double().cpu().numpy(), cpu["rgb"].double().numpy()
+    rep["rgb_max_abs_err"] = float(np.abs(rg - rc).max())
+    rep["rgb_elems_over_1e-4_rel"] = int((np.abs(rg - rc) > 1e-4 * np.abs(rc) + 1e-4 * np.abs(rc).mean()).sum())
+    if "grid" in cpu and "grid" in gpu:
+        gg, gc = gpu["grid"].cpu().numpy(), cpu["grid"].numpy()
+        qg, qc = gpu["calc"].cpu().numpy().astype(bool), cpu["calc"].numpy().astype(bool)
+        rep["queried_gpu"], rep["queried_oracle"] = int(qg.sum()), int(qc.sum())
+        rep["queried_set_mismatch"] = int((qg != qc).sum())
+        rep["sign_mismatch"] = int(((gg > 0.0) != (gc > 0.0)).sum())
+        rep["grid_max_abs_err"] = float(np.abs(gg.astype(np.float64) - gc).max())
+        fg, fc = gpu["faces"].cpu().numpy(), cpu["faces"]
+        rep["mc_faces_gpu"], rep["mc_faces_oracle"] = int(fg.shape[0]), int(fc.shape[0])
+        rep["mc_faces_identical"] = bool(fg.shape == fc.shape and np.array_equal(fg, fc))
+        vg, vc = gpu["verts"].cpu().numpy(), cpu["verts"]
+        rep["mc_verts_gpu"], rep["mc_verts_oracle"] = int(vg.shape[0]), int(vc.shape[0])
+        rep["mc_verts_max_abs_err"] = float(np.abs(vg - vc).max()) if vg.shape == vc.shape else None
+    return rep
 
 
 def pick_threads():
@@ -251,8 +315,24 @@ def pick_threads():
     return best
 
 
+def bench_config(n_rays, world):
+    """The `config` object both arms print (the reference arm runs a bounded sample OF THIS workload)."""
+    return {"workload": "config[1]: one 512x512 synthetic frame per GPU, %d silhouette rays, 8x512 SDF + "
+                        "Deformer(MLP+LBS 129x225x65) + RenderNet; trace times=10 dthr=5e-5; 257^3 "
+                        "coarse-to-fine grid + MC" % n_rays,
+            "rays_per_frame": n_rays, "mc_grid": GRID_N, "l2": "256 MiB flush between timed regions",
+            "parallelism": "frames sharded, dp%d, no data-path collective" % world}
+
+
+def frame_ray_count():
+    from selfreconcode_b200 import synth
+    return int(synth.sphere_pixels(synth.camera(512, 512))[0].shape[0])
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path (oracle port) on host cores, bounded sample."""
+    """--impl reference: the reference's CPU path (oracle port) on host cores.  Same config / metric as the GPU
+    arm; every step is a bounded sample of that frame's rays (the whole frame takes ~25 s per step on the
+    host), plus ONE untimed-in-`value` pass of the same 257^3 grid + MC for the voxel figure."""
     if rank != 0:
         return
     threads = pick_threads()
@@ -265,13 +345,16 @@ def run_reference(args, rank, world):
         vals.append(r["rays_per_sec"])
         ts.append(r["ray_seconds"])
     v = float(np.mean(vals))
+    mc = cpu_reference_sample(256, threads, with_mc=True)
     line = {"impl": "reference", "metric": "rays_per_sec", "value": v, "unit": "rays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(ts)),
+            "mc_voxels_per_sec": mc["mc_voxels_per_sec"], "mc_queried_voxels": mc["mc_queried"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config[1]: 512x512 synthetic frame, 8x512 SDF + Deformer(LBS) + RenderNet; "
-                                   "bounded sample of %d rays per step on host cores" % n},
+            "config": bench_config(frame_ray_count(), max(world, 1)),
             "cpu_baseline": {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
-                             "sample": "%d rays of the frame: OptimizeSurfacePs(times=10)+shading through oracle/oracle.py" % n},
+                             "sample": "%d of the frame's rays per step: OptimizeSurfacePs(times=10) + shading "
+                                       "through oracle/oracle.py (torch fp32 CPU); the 257^3 coarse-to-fine grid + MC "
+                                       "once (mc_voxels_per_sec)" % n},
             "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -342,6 +425,22 @@ def main():
         barrier()
         t_wall = time.perf_counter() - t_wall0
     launches = ops.LAUNCHES
+    # second number: weights change every step (a training loop): weight-norm fold + tensor-core weight packing
+    # + an eager (not graph-replayed) trace are inside the timed region
+    refold_ms = []
+    for _ in range(max(2, args.steps // 2)):
+        flush.zero_()
+        for m in (sc["sdf"], sc["comp"].defs[0], sc["rn"]):
+            m._cache.sig = None
+        a, b = ev(), ev()
+        a.record()
+        ray_part(sc, rays_d, init_d, bi_d)
+        b.record()
+        torch.cuda.synchronize()
+        refold_ms.append(a.elapsed_time(b))
+    ray_part(sc, rays_d, init_d, bi_d)   # back to the steady state (graph captured again)
+    ray_part(sc, rays_d, init_d, bi_d)
+    torch.cuda.synchronize()
     # per-kernel timing of the dominant kernel (trace_kernel): events around the 11 launches
     tk = []
     for _ in range(3):
@@ -415,14 +514,12 @@ def main():
         "metric": "rays_per_sec", "value": total_rays / (ray_t * 1e-3), "unit": "rays/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ray_t + mc_t, "ms_ray_part": ray_t, "ms_mc_part": mc_t,
+        "ms_ray_part_refold": float(np.mean(refold_ms)),
+        "rays_per_sec_refold": n_rays / (float(np.mean(refold_ms)) * 1e-3),
         "mc_voxels_per_sec": world * GRID_N ** 3 / (mc_t * 1e-3),
         "mc_queried_voxels": int(eng.last_num_queried), "mc_vertices": int(v.shape[0]), "mc_faces": int(f.shape[0]),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "config[1]: one 512x512 synthetic frame per GPU, %d silhouette rays, 8x512 SDF + "
-                               "Deformer(MLP+LBS 129x225x65) + RenderNet; trace times=10 dthr=5e-5; 257^3 "
-                               "coarse-to-fine grid + MC" % n_rays,
-                   "rays_per_frame": n_rays, "mc_grid": GRID_N, "l2": "256 MiB flush between timed regions",
-                   "parallelism": "frames sharded, dp%d, no data-path collective" % world},
+        "config": bench_config(n_rays, world),
         "e2e": {"value": total_rays / (e2e_t * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms": e2e_t},
         "gpu_launches": int(launches),
@@ -458,7 +555,12 @@ def main():
     }
     if not args.no_cpu_baseline and world == 1:
         threads = pick_threads()
-        cb = cpu_reference_sample(None, threads, with_mc=True)
+        cb = cpu_reference_sample(None, threads, with_mc=True, rays={k: v for k, v in R.items()}, keep=True)
+        # parity at the benchmark's own size: the GPU results of one more (untimed) step vs the oracle's
+        pts_g, conv_g, rgb_g = ray_part(sc, rays_d, init_d, bi_d)
+        grid_g, v_g, f_g = mc_part(sc, eng)
+        line["parity"] = parity_report(dict(pts=pts_g, conv=conv_g, rgb=rgb_g, grid=grid_g[0, 0],
+                                            calc=eng.last_calculated, verts=v_g, faces=f_g), cb["keep"])
         line["cpu_baseline"] = {"value": cb["rays_per_sec"], "unit": "rays/s", "cores": threads, "kind": "port",
                                 "sample": "all rays of the same frame (trace times=10 + shading) and the same 257^3 "
                                           "coarse-to-fine grid + MC through oracle/ (torch fp32 CPU + C)",

@@ -214,6 +214,8 @@ struct SdfArgs {
   float* grad;
   float* feat;
   int nfeat;
+  const int32_t* index;   // optional list of point ids to evaluate (results land at sdf[id])
+  const int32_t* m_dev;   // device-side length of `index`
 };
 
 template <int T>
@@ -222,7 +224,9 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_kernel(const __grid_constant_
   TileCtx c = make_ctx(smem_raw);
   pipe_init(c.s);
   constexpr int PTS = kTileRows / (T + 1);
-  const long long ntiles = (args.P + PTS - 1) / PTS;
+  long long count = args.P;
+  if (args.m_dev != nullptr) { const long long md = *args.m_dev; count = md < count ? md : count; }
+  const long long ntiles = (count + PTS - 1) / PTS;
   Pipe cp{0, 0};
   Prod prod;
   program_begin(c.s);
@@ -230,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_kernel(const __grid_constant_
   prod.init(blockIdx.x, ntiles, gridDim.x);
   prod.prefill(c.s);
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    load_points<T>(c, tile, args.P, nullptr, args.pts, nullptr, 0);
+    load_points<T>(c, tile, count, args.index, args.pts, nullptr, 0);
     consumer_sync();
     prologue_pe<T>(c, args.net, nullptr, 0);
     LastOut lo{args.feat, args.nfeat, c.row_pt, nullptr};
@@ -862,6 +866,25 @@ int validate_net(const sr_mlp_desc* net, int T) {
   return SR_OK;
 }
 
+// ids of the values within eps of `center` -> list (warp-aggregated append; order is irrelevant
+// to the caller, which writes results back by id)
+__global__ void __launch_bounds__(256)
+band_select_kernel(const float* __restrict__ v, long long n, float center, float eps,
+                   int32_t* __restrict__ list, int32_t* __restrict__ counter) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n_round = (n + 31) / 32 * 32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    const bool hit = i < n && fabsf(v[i] - center) < eps;
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (m == 0u) continue;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (hit) list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+  }
+}
+
 template <typename K>
 int set_smem(K kernel) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -899,6 +922,7 @@ int sr_sdf_forward(const sr_mlp_desc* net, const float* pts, int64_t P, float* s
   if (feat && (nfeat <= 0 || nfeat + 1 > net->layer[net->n_layers - 1].n)) return SR_EINVAL;
   SdfArgs a;
   a.net = *net; a.pts = pts; a.P = P; a.sdf = sdf; a.grad = grad; a.feat = feat; a.nfeat = nfeat;
+  a.index = nullptr; a.m_dev = nullptr;
   if (grad) {
     if ((rc = set_smem(sdf_kernel<3>))) return rc;
     const long long nt = (P + 15) / 16;
@@ -908,6 +932,35 @@ int sr_sdf_forward(const sr_mlp_desc* net, const float* pts, int64_t P, float* s
     const long long nt = (P + 63) / 64;
     sdf_kernel<0><<<grid_for_tiles(nt), kThreads, kDynSmem, s>>>(a);
   }
+  return sr_launch_status();
+}
+
+// Value-only re-evaluation of the points listed in `index` (device-side count `m_dev`, at most P)
+// on this fp32 engine; sdf[index[i]] is overwritten.  Used to decide signs / thresholds of values
+// the tensor-core engine left inside its error band (MCAcc/seg3d_lossless.py:333-346 compares
+// `> balance`; utils/FindSurfacePs.py:120-127 compares `< dthreshold`).
+int sr_sdf_forward_indexed(const sr_mlp_desc* net, const float* pts, int64_t P, const int32_t* index,
+                           const int32_t* m_dev, float* sdf, cudaStream_t s) {
+  int rc = validate_net(net, 0);
+  if (rc) return rc;
+  if (P < 0 || P > 0x7fffffffLL) return SR_EINVAL;
+  if (P == 0) return SR_OK;
+  if (!pts || !sdf || !index || !m_dev) return SR_EINVAL;
+  if (net->d_in != 3 + 6 * net->multires) return SR_EINVAL;
+  SdfArgs a;
+  a.net = *net; a.pts = pts; a.P = P; a.sdf = sdf; a.grad = nullptr; a.feat = nullptr; a.nfeat = 0;
+  a.index = index; a.m_dev = m_dev;
+  if ((rc = set_smem(sdf_kernel<0>))) return rc;
+  const long long nt = (P + 63) / 64;
+  sdf_kernel<0><<<grid_for_tiles(nt), kThreads, kDynSmem, s>>>(a);
+  return sr_launch_status();
+}
+
+int sr_band_select(const float* values, int64_t n, float center, float eps, int32_t* list,
+                   int32_t* counter, cudaStream_t s) {
+  if (!values || !list || !counter || n < 0 || n > 0x7fffffffLL) return SR_EINVAL;
+  if (n == 0) return SR_OK;
+  band_select_kernel<<<sr_grid_for(n, 256, 8), 256, 0, s>>>(values, n, center, eps, list, counter);
   return sr_launch_status();
 }
 

@@ -984,7 +984,11 @@ int sr_tc_linear(const void* A, const void* W, const float* bias, int64_t M, int
   }
 #undef SR_TC_PICK
   if (!kern) return SR_EINVAL;
-  static bool attr_set = false;
+  // cudaFuncSetAttribute is per device: one flag per device ordinal (a process may drive several GPUs)
+  static bool attr_set_dev[64] = {};
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& attr_set = attr_set_dev[cur_dev & 63];
   if (!attr_set) {
 #define SR_TC_BOTH(ACT_, CH_, MUL_)                                                                        \
   {                                                                                                        \

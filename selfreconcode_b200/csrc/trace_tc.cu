@@ -28,6 +28,12 @@ struct MidArgs {
   float* ddef;             // [M][ld] cotangent rows for the translator backward sweep (cols 0..2)
   int ld;
   float* aux;              // [M][8]: loss, state, u[3]
+  // borderline decisions: the tensor-core engine's f / D(p) carry up to ~2.4e-5 / ~1e-5 of error, so a
+  // ray whose test could flip inside (eps_f, eps_a) is NOT decided here: it is appended to `recheck`
+  // and re-tested by the fp32 FFMA engine (sr_trace_step_rev, test-only) before the update kernel runs.
+  int* recheck;            // [P] or null (then the test below is final)
+  int* recheck_count;
+  float eps_f, eps_a;
 };
 
 __global__ void __launch_bounds__(256) trace_mid_kernel(const __grid_constant__ MidArgs a) {
@@ -64,7 +70,13 @@ __global__ void __launch_bounds__(256) trace_mid_kernel(const __grid_constant__ 
       const float n_u = sqrtf(ux * ux + uy * uy + uz * uz);
       const float sang = n_up / n_u;
       const float ang = asinf(sang) * 180.0f / 3.14159265358979323846f;
-      const bool done = (fabsf(f) < a.tp.dthreshold) && (ang < a.tp.athreshold);
+      bool done = (fabsf(f) < a.tp.dthreshold) && (ang < a.tp.athreshold);
+      if (a.recheck != nullptr) {
+        const bool maybe = (fabsf(f) < a.tp.dthreshold + a.eps_f) && (ang < a.tp.athreshold + a.eps_a);
+        const bool sure = (fabsf(f) < a.tp.dthreshold - a.eps_f) && (ang < a.tp.athreshold - a.eps_a);
+        if (maybe && !sure) a.recheck[atomicAdd(a.recheck_count, 1)] = (int)gp;
+        done = sure;
+      }
       float u[3] = {0.f, 0.f, 0.f}, loss = 0.f;
       int state = 0;
       if (done) {
@@ -118,6 +130,7 @@ struct UpdArgs {
   float pw_d[16];
   int* active_out;
   int* counter_out;
+  const unsigned char* converged;   // rays the fp32 re-test declared done after trace_mid (or null)
 };
 
 __device__ __forceinline__ void pe_chain(const float* g, const float* gk, const float x[3], int multires,
@@ -146,6 +159,7 @@ __global__ void __launch_bounds__(256) trace_update_kernel(const __grid_constant
     const float* ax = a.aux + i * 8;
     if (__float_as_int(ax[1]) != 1) continue;
     const long long gp = a.index ? (long long)a.index[i] : i;
+    if (a.converged != nullptr && a.converged[gp]) continue;
     const float x[3] = {a.pts[gp * 3], a.pts[gp * 3 + 1], a.pts[gp * 3 + 2]};
     float g[3] = {ax[2], ax[3], ax[4]};  // direct term u (d p' / d p = I + d off / d p)
     pe_chain(a.gs + i * a.gs_ld, a.gskip ? a.gskip + i * a.gk_ld : nullptr, x, a.mr_s, a.pw_s, g);
@@ -303,15 +317,17 @@ int sr_tc_render_embed(int64_t P, const float* pts, const float* views, const fl
 int sr_tc_trace_mid(const int32_t* index, const int32_t* m_dev, int64_t P, const float* pts,
                     const float* rays, const int64_t* batch_inds, const float* f, const float* off,
                     const sr_lbs_params* lbs, const sr_trace_params* tp, int do_update,
-                    uint8_t* converged, float* dsdf, float* ddef, int ld, float* aux, cudaStream_t s) {
+                    uint8_t* converged, float* dsdf, float* ddef, int ld, float* aux,
+                    int32_t* recheck, int32_t* recheck_count, float eps_f, float eps_a, cudaStream_t s) {
   if (!pts || !rays || !f || !tp || !converged || !dsdf || !aux || P <= 0 || ld < 8) return SR_EINVAL;
+  if ((recheck != nullptr) != (recheck_count != nullptr) || eps_f < 0.f || eps_a < 0.f) return SR_EINVAL;
   MidArgs a;
   a.index = index; a.m_dev = m_dev; a.P = P; a.pts = pts; a.rays = rays;
   a.batch_inds = (const long long*)batch_inds; a.f = f; a.off = off;
   a.has_lbs = lbs ? 1 : 0;
   if (lbs) a.lbs = *lbs;
   a.tp = *tp; a.do_update = do_update; a.converged = converged; a.dsdf = dsdf; a.ddef = ddef; a.ld = ld;
-  a.aux = aux;
+  a.aux = aux; a.recheck = recheck; a.recheck_count = recheck_count; a.eps_f = eps_f; a.eps_a = eps_a;
   trace_mid_kernel<<<sr_grid_for(P * 32, 256, 8), 256, 0, s>>>(a);
   return sr_launch_status();
 }
@@ -319,13 +335,14 @@ int sr_tc_trace_mid(const int32_t* index, const int32_t* m_dev, int64_t P, const
 int sr_tc_trace_update(const int32_t* index, const int32_t* m_dev, int64_t P, float* pts,
                        const float* gs, int gs_ld, const float* gskip, int gk_ld, const float* gd,
                        int gd_ld, const float* aux, int mr_s, const float* pw_s, int mr_d,
-                       const float* pw_d, int32_t* active_out, int32_t* counter_out, cudaStream_t s) {
+                       const float* pw_d, int32_t* active_out, int32_t* counter_out,
+                       const uint8_t* converged, cudaStream_t s) {
   if (!pts || !gs || !aux || !active_out || !counter_out || !pw_s || P <= 0) return SR_EINVAL;
   UpdArgs a;
   a.index = index; a.m_dev = m_dev; a.P = P; a.pts = pts; a.gs = gs; a.gs_ld = gs_ld; a.gskip = gskip;
   a.gk_ld = gk_ld; a.gd = gd; a.gd_ld = gd_ld; a.aux = aux; a.mr_s = mr_s; a.mr_d = mr_d;
   for (int i = 0; i < 16; ++i) { a.pw_s[i] = i < mr_s ? pw_s[i] : 0.f; a.pw_d[i] = (pw_d && i < mr_d) ? pw_d[i] : 0.f; }
-  a.active_out = active_out; a.counter_out = counter_out;
+  a.active_out = active_out; a.counter_out = counter_out; a.converged = converged;
   trace_update_kernel<<<sr_grid_for(P, 256, 8), 256, 0, s>>>(a);
   return sr_launch_status();
 }

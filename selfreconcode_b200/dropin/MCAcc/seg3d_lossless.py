@@ -67,6 +67,7 @@ class Seg3dLossless(nn.Module):
         init_coords = create_grid3D(0, resolutions[-1] - 1, steps=resolutions[0], device="cpu")
         self.register_buffer('init_coords', init_coords.unsqueeze(0))
         self.last_num_queried = 0
+        self.last_calculated = None
 
     # MCAcc/seg3d_lossless.py:89-108
     def batch_eval(self, coords, **kwargs):
@@ -128,4 +129,5 @@ class Seg3dLossless(nn.Module):
                     break
                 flag = conflicts.view(D, H, W)
         self.last_num_queried = nq
+        self.last_calculated = calculated   # [fD,fH,fW] bool: the final-grid voxels that were queried
         return occ.view(1, 1, *occ.shape)

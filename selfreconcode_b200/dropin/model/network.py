@@ -94,8 +94,11 @@ class ImplicitNetwork(nn.Module):
     def _pe_weights(self, ratio):
         return ops.annealing_weights(self.multires, ratio)
 
-    def forward_fused(self, input, ratio, want_grad=False, want_feat=True):
-        """-> (sdf [P,d_out], grad [P,3] | None, feat | None) without building a graph."""
+    def forward_fused(self, input, ratio, want_grad=False, want_feat=True, refine_about=0.0):
+        """-> (sdf [P,d_out], grad [P,3] | None, feat | None) without building a graph.
+        Large value-only batches run on the tensor-core engine; values within its error band of
+        `refine_about` (the level a caller compares against: the MC balance value) are then re-evaluated
+        on the fp32 engine so that the comparison's outcome is the fp32 one (None disables it)."""
         if self.d_out != 1:
             raise RuntimeError("ImplicitNetwork: fused path supports d_out == 1")
         r = ratio_value(ratio, "sdfRatio")
@@ -109,6 +112,8 @@ class ImplicitNetwork(nn.Module):
             # large value-only batches (the 257^3 / 513^3 grid queries): tensor-core engine
             # (tcgen05 split-BF16 GEMM per layer, csrc/tc_gemm.cu)
             sdf = ops.tc_mlp_forward(net, pts, ch=1, n_out=1)
+            if refine_about is not None and ops.TC_REFINE:
+                ops.sdf_refine_band(net, pts.contiguous().float(), sdf.view(-1), float(refine_about))
             return sdf.view(-1, 1), None, None
         sdf, grad, feat = ops.sdf_forward(net, pts, want_grad, nfeat)
         return sdf.view(-1, 1), grad, feat

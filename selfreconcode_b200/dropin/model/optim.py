@@ -76,7 +76,8 @@ class OptimNetwork(nn.Module):
         def query_func(points):
             with torch.no_grad():
                 if hasattr(sdf, "forward_fused"):  # value only: skip the 256-d feature head
-                    return sdf.forward_fused(points.reshape(-1, 3), ratio, False, False)[0].reshape(1, 1, -1)
+                    return sdf.forward_fused(points.reshape(-1, 3), ratio, False, False,
+                                             refine_about=balance_value)[0].reshape(1, 1, -1)
                 return sdf.forward(points.reshape(-1, 3), ratio).reshape(1, 1, -1)
 
         if engine is None:

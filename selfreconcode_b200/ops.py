@@ -22,6 +22,13 @@ import os as _os
 TC_ENABLED = _os.environ.get("SELFRECON_B200_TC", "1") != "0"
 TC_MIN_POINTS = int(_os.environ.get("SELFRECON_B200_TC_MIN_POINTS", "16384"))
 
+# Borderline decisions on tensor-core values are re-taken on the fp32 FFMA engine:
+# TC_EPS_F bounds the engine's absolute error on an SDF value (measured 2.4e-5 against fp64, csrc/tc_gemm.cu),
+# TC_EPS_A (degrees) the error of the ray/point angle that follows from D(p)'s.
+TC_EPS_F = float(_os.environ.get("SELFRECON_B200_TC_EPS_F", "4e-5"))
+TC_EPS_A = float(_os.environ.get("SELFRECON_B200_TC_EPS_A", "1e-3"))
+TC_REFINE = _os.environ.get("SELFRECON_B200_TC_REFINE", "1") != "0"
+
 import itertools as _it
 _uid_counter = _it.count()
 LAUNCHES = 0  # kernels launched by this module since it was last reset (bench.py reads it)
@@ -346,6 +353,33 @@ def sdf_forward(net, pts, want_grad=False, nfeat=0):
     return sdf, grad, feat
 
 
+_band_scratch = {}
+
+
+def sdf_refine_band(net, pts, sdf, center=0.0, eps=None):
+    """In place: every sdf[i] with |sdf[i] - center| < eps is re-evaluated by the fp32 FFMA engine
+    (device-side list + count, no host sync).  `net` is the FusedMLP the values came from."""
+    _need_cuda(pts, sdf)
+    eps = TC_EPS_F if eps is None else float(eps)
+    P = sdf.numel()
+    if P == 0:
+        return sdf
+    dev = sdf.device
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        key = (dev.index, torch.cuda.current_stream().cuda_stream)
+        buf = _band_scratch.get(key)
+        if buf is None or buf.numel() < P + 1:
+            buf = torch.empty((max(P + 1, 1 << 16),), dtype=torch.int32, device=dev)
+            _band_scratch[key] = buf
+        cnt, lst = buf[0:1], buf[1:]
+        cnt.zero_()
+        check(lib.sr_band_select(_p(sdf), P, float(center), eps, _p(lst), _p(cnt), _stream()), "band_select")
+        check(lib.sr_sdf_forward_indexed(C.byref(net.desc), _p(pts), P, _p(lst), _p(cnt), _p(sdf), _stream()),
+              "sdf_forward_indexed")
+    return sdf
+
+
 class LbsState:
     """Device-side LBS inputs: channels-last weight volume + per-frame bone transforms."""
 
@@ -437,10 +471,28 @@ def render_forward(net, pts, normals, views, feat):
 _scratch = {}
 
 
+_host_cache = {}
+
+
+def _host_floats(t):
+    """Host copy of a small device tensor (camera centre), cached by (storage, version): the blocking
+    device->host read happens once per tensor value, not once per trace."""
+    if not t.is_cuda:
+        return tuple(float(x) for x in t.detach().reshape(-1).tolist())
+    key = (t.device.index, t.data_ptr(), t._version, t.numel())
+    v = _host_cache.get(key)
+    if v is None:
+        if len(_host_cache) > 64:
+            _host_cache.clear()
+        v = tuple(float(x) for x in t.detach().reshape(-1).tolist())
+        _host_cache[key] = v
+    return v
+
+
 def _trace_scratch(dev):
-    """act'(z) stash of the reverse-mode tracer (one region per SM, reused across calls on the
-    same stream order)."""
-    key = dev.index
+    """act'(z) stash of the reverse-mode tracer (one region per SM), one per (device, stream) so that
+    traces running concurrently on two streams do not share it."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
     if key not in _scratch:
         n = _lib.load().sr_trace_scratch_bytes()
         _scratch[key] = torch.empty((n // 4,), dtype=torch.float32, device=dev)
@@ -474,7 +526,7 @@ def trace_surface_points(sdf_net, def_net, lbs, cam_pos, rays, init_pts, batch_i
     lists = [torch.empty((P,), dtype=torch.int32, device=dev) for _ in range(2)]
     counters = torch.zeros((times + 3,), dtype=torch.int32, device=dev)
     tp = TraceParams()
-    cp = [float(x) for x in cam_pos.detach().view(-1).tolist()]
+    cp = _host_floats(cam_pos)
     for i in range(3):
         tp.cam_pos[i] = cp[i]
     tp.dthreshold, tp.athreshold, tp.w1, tp.w2 = float(dthreshold), float(athreshold), float(w1), float(w2)
@@ -811,6 +863,10 @@ class _TcTraceCtx:
         self.lbsA = torch.empty((n_frames, 24, 4, 4), dtype=torch.float32, device=dev)
         self.lbsT = torch.empty((n_frames, 3), dtype=torch.float32, device=dev)
         self.lbs_params = LbsParams()
+        # borderline rays of each iteration, re-tested on the fp32 engine (one list, one count per iteration)
+        self.recheck = torch.empty((P,), dtype=torch.int32, device=dev)
+        self.recheck_counts = torch.empty((times + 1,), dtype=torch.int32, device=dev)
+        self.rev_scratch = _trace_scratch(dev)
         self.graph = None
         self.sig = None
         self.calls = 0
@@ -832,6 +888,10 @@ def _tc_trace_body(lib, G, sdf_net, def_net, ts, td, tp, P, times, condlen, has_
     conv.zero_()
     counters.zero_()
     counters[0:1].fill_(P)
+    refine = TC_REFINE
+    if refine:
+        G.recheck_counts.zero_()
+    dref = C.byref(def_net.desc) if def_net is not None else None
     for it in range(times + 1):
         idx = lists[(it + 1) & 1] if it > 0 else None
         a_out = lists[it & 1] if it < times else None
@@ -847,8 +907,17 @@ def _tc_trace_body(lib, G, sdf_net, def_net, ts, td, tp, P, times, condlen, has_
         check(lib.sr_tc_trace_mid(_p(idx), _p(m_dev), P, _p(pts), _p(rays), _p(bi), _p(B.f),
                                   _p(B.off) if def_net is not None else None, lbs_ref, C.byref(tp),
                                   1 if a_out is not None else 0, _p(conv), _p(B.cot_s),
-                                  _p(B.cot_d) if def_net is not None else None, 32, _p(B.aux), _stream()),
+                                  _p(B.cot_d) if def_net is not None else None, 32, _p(B.aux),
+                                  _p(G.recheck) if refine else None,
+                                  _p(G.recheck_counts[it:it + 1]) if refine else None,
+                                  TC_EPS_F if refine else 0.0, TC_EPS_A if refine else 0.0, _stream()),
               "tc_trace_mid")
+        if refine:
+            # fp32 re-test of the borderline rays (test-only launch: no update, marks converged[])
+            check(lib.sr_trace_step_rev(C.byref(sdf_net.desc), dref, lbs_ref, C.byref(tp), _p(pts), _p(rays),
+                                        _p(bi), _p(conds), condlen, P, _p(G.recheck), None,
+                                        _p(G.recheck_counts), it, _p(conv), _p(G.rev_scratch), _stream()),
+                  "trace_step_rev")
         if a_out is None:
             break
         # ---- reverse sweeps + update
@@ -862,7 +931,8 @@ def _tc_trace_body(lib, G, sdf_net, def_net, ts, td, tp, P, times, condlen, has_
                                      _p(B.gd) if def_net is not None else None,
                                      B.gd.shape[1] if def_net is not None else 0, _p(B.aux), ds.multires,
                                      pw_s, dd.multires if dd is not None else 0, pw_d, _p(a_out),
-                                     _p(counters[it + 1:it + 2]), _stream()), "tc_trace_update")
+                                     _p(counters[it + 1:it + 2]), _p(conv) if refine else None, _stream()),
+              "tc_trace_update")
 
 
 def trace_surface_points_tc(sdf_net, def_net, lbs, cam_pos, rays, init_pts, batch_inds, conds,
@@ -885,7 +955,7 @@ def trace_surface_points_tc(sdf_net, def_net, lbs, cam_pos, rays, init_pts, batc
     lib = _lib.load()
     condlen = conds.shape[-1] if conds is not None else 0
     n_frames = lbs.A.shape[0] if lbs is not None else (conds.shape[0] if conds is not None else 1)
-    cp = tuple(float(x) for x in cam_pos.detach().view(-1).tolist())
+    cp = _host_floats(cam_pos)
     ds, dd = sdf_net.desc, (def_net.desc if def_net is not None else None)
     # buffers depend on shapes only; the captured graph also on everything a launch bakes in
     key = (dev.index, P, tuple(ds.layer[i].n for i in range(ds.n_layers)),
@@ -894,7 +964,8 @@ def trace_surface_points_tc(sdf_net, def_net, lbs, cam_pos, rays, init_pts, batc
     sig = (sdf_net.uid, def_net.uid if def_net is not None else -1,
            lbs.ws_cl.data_ptr() if lbs is not None else 0, cp, float(dthreshold), float(athreshold),
            float(w1), float(w2), tuple(ds.pe_w[i] for i in range(ds.multires)),
-           tuple(dd.pe_w[i] for i in range(dd.multires)) if dd is not None else ())
+           tuple(dd.pe_w[i] for i in range(dd.multires)) if dd is not None else (),
+           TC_REFINE, TC_EPS_F, TC_EPS_A)
     G = _tc_trace_ctx.get(key)
     if G is None:
         if len(_tc_trace_ctx) >= 4:
