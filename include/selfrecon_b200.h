@@ -299,6 +299,13 @@ int sr_tc_linear(const void* A, const void* W, const float* bias, int64_t M, int
                  int out_col0, int out_n, float* dstash, const void* mul_tiles, int mul_K, int mul_act,
                  float mul_scale, const int32_t* m_dev, cudaStream_t s);
 
+/* Batched 3x3 singular values (descending) + right singular vectors (columns of V, may be NULL), and the
+ * backward of a function of the VALUES: gJ = sum_i gS_i u_i v_i^T.  Replaces `torch.svd(Jacobs.cpu())` of the
+ * def_regu block (model/network.py:573-575).  J, V, gJ: [n,3,3] row-major; S, gS: [n,3]. */
+int sr_svals3x3_f32(const float* J, float* S, float* V, int64_t n, cudaStream_t s);
+int sr_svals3x3_bwd_f32(const float* J, const float* S, const float* V, const float* gS, float* gJ, int64_t n,
+                        cudaStream_t s);
+
 /* Borderline decisions.  The tensor-core engine's values carry up to ~2.4e-5 of absolute error, so
  * a sign (`> balance`, MCAcc/seg3d_lossless.py:333-346) or threshold (`< dthreshold`,
  * utils/FindSurfacePs.py:120-127) decision on a value inside that band is re-taken on the fp32 FFMA engine:

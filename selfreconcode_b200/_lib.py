@@ -104,6 +104,8 @@ SIGNATURES = {
                                   stream_t]),
     "sr_tc_trace_update": (C.c_int, [c_f, c_f, i64, c_f, c_f, i32, c_f, i32, c_f, i32, c_f, i32,
                                      C.POINTER(f32), i32, C.POINTER(f32), c_f, c_f, c_f, stream_t]),
+    "sr_svals3x3_f32": (C.c_int, [c_f, c_f, c_f, i64, stream_t]),
+    "sr_svals3x3_bwd_f32": (C.c_int, [c_f, c_f, c_f, c_f, c_f, i64, stream_t]),
     "sr_band_select": (C.c_int, [c_f, i64, f32, f32, c_f, c_f, stream_t]),
     "sr_sdf_forward_indexed": (C.c_int, [C.POINTER(MlpDesc), c_f, i64, c_f, c_f, c_f, stream_t]),
     "sr_tc_shade_point": (C.c_int, [i64, c_f, c_f, c_f, c_f, i32, c_f, C.POINTER(LbsParams), c_f, c_f, c_f,

@@ -66,6 +66,15 @@ class Seg3dLossless(nn.Module):
                 f"resolution {resolution} need to be odd becuase of align_corner."
         init_coords = create_grid3D(0, resolutions[-1] - 1, steps=resolutions[0], device="cpu")
         self.register_buffer('init_coords', init_coords.unsqueeze(0))
+        # state_dict parity with the reference's engine (seg3d_lossless.py:67-82): a `calculated` mask of the
+        # final grid (this implementation's working mask, exposed after forward()), the 27 neighbour offsets and
+        # the four box filters.  The dilation here is a byte kernel, so the filters are never applied.
+        fW, fH, fD = [int(v) for v in resolutions[-1]]
+        self.register_buffer('calculated', torch.zeros((fD, fH, fW), dtype=torch.bool))
+        o = torch.tensor([-1, 0, 1])
+        self.register_buffer('gird8_offsets', torch.stack(torch.meshgrid([o, o, o], indexing="ij")).int().view(3, -1).t())
+        for k in (3, 5, 7, 9):
+            setattr(self, 'smooth_conv%dx%d' % (k, k), SmoothConv3D(in_channels=1, out_channels=1, kernel_size=k))
         self.last_num_queried = 0
         self.last_calculated = None
 
@@ -90,7 +99,8 @@ class Seg3dLossless(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("Seg3dLossless: module must live on a CUDA device (no CPU path)")
         fW, fH, fD = [int(v) for v in self.resolutions[-1]]
-        calculated = torch.zeros((fD, fH, fW), dtype=torch.bool, device=dev)
+        calculated = self.calculated
+        calculated.zero_()
         bal = self.balance_value
         bmin = [float(v) for v in self.b_min.view(-1).tolist()]
         bmax = [float(v) for v in self.b_max.view(-1).tolist()]

@@ -60,3 +60,28 @@ class RectifiedPerspectiveCameras:
         th = torch.min(th, ang([0., (H - cy) / fy, 1.], [0., (H + pixoffset - cy) / fy, 1.]))
         th = torch.min(th, ang([0., -cy / fy, 1.], [0., (pixoffset - cy) / fy, 1.]))
         return th.item()
+
+
+class PointsRendererWithFrags(torch.nn.Module):
+    """Soft point-cloud silhouette renderer that also returns the rasteriser's fragments
+    (model/CameraMine.py:283-320): weight 1 - d^2/r^2 per (pixel, point) pair, composited by the given
+    compositor.  Works with any rasteriser / compositor pair following pytorch3d's protocol
+    (`rasterizer(point_clouds) -> fragments(idx, dists)`, `raster_settings.radius`)."""
+
+    def __init__(self, rasterizer, compositor):
+        super().__init__()
+        self.rasterizer = rasterizer
+        self.compositor = compositor
+
+    def to(self, device):
+        self.rasterizer = self.rasterizer.to(device)
+        self.compositor = self.compositor.to(device)
+        return self
+
+    def forward(self, point_clouds, **kwargs):
+        frags = self.rasterizer(point_clouds, **kwargs)
+        r = self.rasterizer.raster_settings.radius
+        weights = 1 - frags.dists.permute(0, 3, 1, 2) / (r * r)
+        images = self.compositor(frags.idx.long().permute(0, 3, 1, 2), weights,
+                                 point_clouds.features_packed().permute(1, 0), **kwargs)
+        return images.permute(0, 2, 3, 1), frags

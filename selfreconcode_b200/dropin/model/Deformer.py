@@ -284,3 +284,43 @@ class LBSkinner(nn.Module):
         T = torch.einsum('pj,pjk->pk', ps_ws, A.view(batch_size, 24, 16)[batch_inds]).view(-1, 4, 4)
         v = torch.matmul(T, F.pad(ps, (0, 1), mode='constant', value=1).unsqueeze(-1))[:, :3, 0]
         return v + trans[batch_inds]
+
+
+def smooth_weights(weights, times=3):
+    """The Deformer-module variant of the volume smoother (model/Deformer.py:234-244): same damped
+    6-neighbour pass as utils.LBSWsmpl.smooth_weights but WITHOUT zeroing small weights."""
+    for _ in range(times):
+        c = weights[:, :, 1:-1, 1:-1, 1:-1]
+        mean = (weights[:, :, 2:, 1:-1, 1:-1] + weights[:, :, :-2, 1:-1, 1:-1] +
+                weights[:, :, 1:-1, 2:, 1:-1] + weights[:, :, 1:-1, :-2, 1:-1] +
+                weights[:, :, 1:-1, 1:-1, 2:] + weights[:, :, 1:-1, 1:-1, :-2]) / 6.0
+        weights[:, :, 1:-1, 1:-1, 1:-1] = (c - mean) * 0.7 + mean
+        weights = weights / weights.sum(1, keepdim=True)
+    return weights
+
+
+def compute_lbswField(bmins, bmaxs, resolutions, smpl_verts, smpl_ws, align_corners=False,
+                      mean_neighbor=5, smooth_times=30):
+    """model/Deformer.py:246-284 (the copy getOptNet's initialiser uses: no small-weight cut)."""
+    from utils.LBSWsmpl import compute_lbswField as _field
+    return _field(bmins, bmaxs, resolutions, smpl_verts, smpl_ws, align_corners, mean_neighbor,
+                  smooth_times, smooth=smooth_weights)
+
+
+def initialLBSkinner(gender, shape, pose, resolution, bmins=None, bmaxs=None):
+    """One-time construction of the LBS field from the SMPL body model (model/Deformer.py:286-296):
+    posed template vertices -> (adaptive) box -> 30-NN skin-weight volume -> LBSkinner.
+    Needs the reference's `smpl_pytorch` package and the SMPL model files (licensed assets,
+    not part of this repository): imported lazily so the module loads without them."""
+    from smpl_pytorch.SMPL import getSMPL
+    smpl = getSMPL(gender).to(shape.device)
+    Js, _ = smpl.skeleton(shape.view(1, -1), True)
+    verts, _, _ = smpl(shape.view(1, -1), pose.view(1, 24, 3), True)
+    if bmins is None or bmaxs is None:
+        margin = np.array([0.15, 0.15, 0.20], dtype=np.float32)
+        bmins = (verts[0].min(0)[0].cpu().numpy() - margin).tolist()
+        bmaxs = (verts[0].max(0)[0].cpu().numpy() + margin).tolist()
+    ws = compute_lbswField(bmins, bmaxs, resolution, verts.view(6890, 3), smpl.weight.view(6890, 24),
+                           align_corners=False, mean_neighbor=30, smooth_times=30)
+    skinner = LBSkinner(ws, bmins, bmaxs, Js, smpl.parents, init_pose=pose, align_corners=False)
+    return skinner, verts.view(6890, 3), torch.tensor(smpl.faces, dtype=torch.long, device=verts.device)

@@ -168,3 +168,12 @@ def getTmpSdf(device, multires, bias=0.6, feature_vector_size=256):
                           dims=[512] * 8, geometric_init=True, bias=bias, skip_in=[4],
                           weight_norm=True, multires=multires)
     return net.to(device)
+
+
+def __getattr__(name):
+    """`model.network.OptimNetwork` / `.getOptNet` (where the reference defines them, network.py:149,828)
+    resolve to the orchestration module; looked up lazily because that module imports this one."""
+    if name in ("OptimNetwork", "getOptNet"):
+        from . import optim
+        return getattr(optim, name)
+    raise AttributeError(name)

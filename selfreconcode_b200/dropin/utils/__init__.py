@@ -1,7 +1,9 @@
-"""Drop-in `utils` package: the hot-path helpers the reference's modules import by `import utils`
-(model/network.py:8): ray/surface finder, Jacobian / cardinal-ray / normal helpers, small math."""
+"""Drop-in `utils` package (reference: utils/__init__.py:1-3 re-exports LBSWsmpl.compute_lbswField,
+FindSurfacePs.* and utils.*): the ray/surface finder, Jacobian / cardinal-ray / normal helpers, small
+math, and the driver-facing config / checkpoint helpers."""
 from . import FindSurfacePs as _find
 from . import utils as _math
+from .LBSWsmpl import compute_lbswField
 
 for _mod in (_find, _math):
     for _name in dir(_mod):

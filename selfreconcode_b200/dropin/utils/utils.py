@@ -24,6 +24,28 @@ class FastDiff3x3MinvFunction(Function):
         return Fast3x3Minv_backward(grad_input.contiguous(), invs), None
 
 
+class SingularValues3x3Function(Function):
+    """Singular values of [P,3,3] matrices on the device (csrc/svals3x3.cu) with the first-order backward
+    a spectral loss needs; stands in for `torch.svd(J.cpu())[1]` (model/network.py:573-575)."""
+
+    @staticmethod
+    def forward(ctx, J):
+        Jc = J.detach().contiguous().float().view(-1, 3, 3)
+        S, V = ops.svals3x3(Jc, want_v=True)
+        ctx.save_for_backward(Jc, S, V)
+        ctx.shape = J.shape
+        return S
+
+    @staticmethod
+    def backward(ctx, gS):
+        Jc, S, V = ctx.saved_tensors
+        return ops.svals3x3_backward(Jc, S, V, gS).view(ctx.shape)
+
+
+def singular_values_3x3(J):
+    return SingularValues3x3Function.apply(J)
+
+
 def quat2mat(quat):
     q = quat / quat.norm(p=2, dim=1, keepdim=True)
     w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
@@ -162,3 +184,119 @@ def shade_rays(sdf, deformer, netRender, ps, rays, defconds, batch_inds, ratio):
         crays, defVs = compute_cardinal_rays(deformer, ps, rays, defconds, batch_inds, ratio, 'test')
         rgb = compute_netRender_color(netRender, ps, defVs, nx, crays, feat, None, ratio)
     return nx, crays, rgb
+
+
+# ------------------------------------------------------------------------------------------------
+# Driver-facing helpers: what train.py / infer.py call on `utils` around the step
+# (reference: utils/utils.py:174-316).  Plain torch; no third-party imports at module scope.
+# ------------------------------------------------------------------------------------------------
+def compute_face_areas(verts, faces):
+    """verts [N,V,3], faces [F,3] or [N,F,3] -> triangle areas [N,F] (utils/utils.py:175-186)."""
+    n = verts.shape[0]
+    if faces.dim() == 2:
+        faces = faces.unsqueeze(0).expand(n, -1, 3)
+    assert faces.shape[0] == n and verts.shape[-1] == faces.shape[-1]
+    tri = torch.gather(verts, 1, faces.reshape(n, -1, 1).expand(-1, -1, 3)).reshape(n, faces.shape[1], 3, 3)
+    return torch.linalg.cross(tri[:, :, 1] - tri[:, :, 0], tri[:, :, 2] - tri[:, :, 0], dim=-1).norm(dim=-1) * 0.5
+
+
+def compute_fnorms(verts, tri_fs):
+    """Unit face normals; verts [V,3] or [B,V,3] (utils/utils.py:189-199)."""
+    a, b, c = (verts.index_select(-2, tri_fs[:, i]) for i in range(3))
+    n = torch.linalg.cross(b - a, c - a, dim=-1)
+    return n / n.norm(2, -1, keepdim=True).clamp(min=1.e-6)
+
+
+def compute_vnorms(verts, tri_fs, vertex_index, face_index):
+    """Vertex normals as the normalised sum of incident face normals (utils/utils.py:224-230);
+    `vertex_index[i]` / `face_index[i]` list every (vertex, incident face) pair."""
+    fn = compute_fnorms(verts, tri_fs).index_select(-2, face_index)
+    out = torch.zeros(verts.shape, dtype=verts.dtype, device=verts.device).index_add_(verts.dim() - 2, vertex_index, fn)
+    return out / out.norm(2, -1, keepdim=True).clamp(min=1.e-6)
+
+
+def DCTBasis(k, N):
+    assert k < N
+    n = torch.arange(N, dtype=torch.float64)
+    scale = (1. / np.sqrt(float(N))) if k == 0 else np.sqrt(2. / float(N))
+    return (torch.cos(np.pi * (n + 0.5) * k / float(N)) * scale).float()
+
+
+def DCTNullSpace(k, N):
+    """Rows k..N-1 of the orthonormal DCT-II basis: the temporal high-frequency space the pose
+    trajectories are penalised in (model/network.py:585-593)."""
+    return torch.stack([DCTBasis(i, N) for i in range(k, N)])
+
+
+def DCTSpace(k, N):
+    return torch.stack([DCTBasis(i, N) for i in range(0, k)])
+
+
+def _new_engine(like, resolutions):
+    from MCAcc import Seg3dLossless
+    return Seg3dLossless(query_func=None, b_min=like.b_min, b_max=like.b_max, resolutions=resolutions,
+                         align_corners=False, balance_value=0.0, visualize=False, debug=False,
+                         use_cuda_impl=False, faster=False).to(like.b_min.device)
+
+
+def set_hierarchical_config(conf, name, optNet, dataloader, resolutions):
+    """Switches the optimisation to hierarchy level `name` ('coarse' / 'medium' / 'fine'): new batch size,
+    the level's loss / train config picked up at the next remesh, a new coarse-to-fine MC engine over the
+    same box (utils/utils.py:237-256)."""
+    bs = conf.get_int('train.' + name + '.point_render.batch_size')
+    dataloader = torch.utils.data.DataLoader(dataloader.dataset, bs, sampler=dataloader.sampler,
+                                             num_workers=dataloader.num_workers)
+    optNet.next_conf = conf.get_config('loss_' + name)
+    optNet.next_train_conf = conf.get_config('train.' + name)
+    optNet.engine = _new_engine(optNet.engine, resolutions)
+    return optNet, dataloader
+
+
+def save_model(name, epoch, optNet, dataset):
+    """`latest.pth` layout (utils/utils.py:257-264): epoch, model_state_dict, the camera tensors by
+    their dataset names, per-frame poses / trans, shape, and the two latent-code tables."""
+    out = {"epoch": epoch, "model_state_dict": optNet.state_dict()}
+    out.update(dataset.camera_params)
+    out.update({'poses': dataset.poses, 'trans': dataset.trans, 'shape': dataset.shape,
+                'dcond': dataset.conds[0], 'rcond': dataset.conds[1]})
+    torch.save(out, name)
+
+
+def _cameras_from(dataset, n, device):
+    from model.CameraMine import RectifiedPerspectiveCameras
+    cam = dataset.camera_params
+    return RectifiedPerspectiveCameras(cam['focal_length'].view(1, 2).expand(n, 2),
+                                       cam['princeple_points'].view(1, 2).expand(n, 2),
+                                       quat2mat(cam['cam2world_coord_quat'].view(1, 4)).expand(n, 3, 3),
+                                       cam['world2cam_coord_trans'].view(1, 3).expand(n, 3),
+                                       image_size=[(dataset.W, dataset.H)]).to(device)
+
+
+def load_model(name, optNet, dataset, device, subsdfmodel=None, model_rm_prefix=None):
+    """Inverse of save_model (utils/utils.py:266-316): engine buffers and the skin-weight volume are not
+    restored (the volume comes from initial_skinner_*.pth), optional key-prefix removal, optional SDF
+    substitution from a bare state_dict; dataset tensors keep their requires_grad flags."""
+    saved = torch.load(name, map_location='cpu')
+    state = {k: v for k, v in saved["model_state_dict"].items() if 'engine.' not in k}
+    if model_rm_prefix:
+        state = {k: v for k, v in state.items() if not any(k.startswith(p) for p in model_rm_prefix)}
+    if subsdfmodel is not None:
+        sub = torch.load(subsdfmodel, map_location='cpu')
+        state = {k: v for k, v in state.items() if 'sdf.' not in k}
+        state.update({'sdf.' + k: v for k, v in sub.items()})
+    state = {k: v for k, v in state.items() if 'deformer.defs.1.ws' not in k}
+    optNet.load_state_dict(state, strict=False)
+    optNet = optNet.to(device)
+    for i, key in enumerate(('dcond', 'rcond')):
+        if key in saved:
+            dataset.conds[i] = saved[key].requires_grad_()
+    for key in ('poses', 'trans', 'shape'):
+        keep = getattr(dataset, key).requires_grad
+        setattr(dataset, key, saved[key].requires_grad_(keep))
+        if key != 'shape':
+            assert dataset.frame_num <= getattr(dataset, key).shape[0]
+    dataset.camera_params = {k: saved[k].requires_grad_(v.requires_grad) for k, v in dataset.camera_params.items()}
+    ras = optNet.maskRender.rasterizer
+    n = getattr(ras.cameras, "_N", None) or ras.cameras.R.shape[0]
+    ras.cameras = _cameras_from(dataset, n, device)
+    return optNet, dataset

@@ -83,6 +83,28 @@ def minv3x3_backward(grads, invs):
     return outs
 
 
+def svals3x3(J, want_v=True):
+    """J [n,3,3] f32 CUDA -> (singular values [n,3] descending, V [n,3,3] | None)."""
+    _need_cuda(J)
+    J = J.contiguous().float()
+    n = J.shape[0]
+    S = torch.empty((n, 3), dtype=torch.float32, device=J.device)
+    V = torch.empty((n, 3, 3), dtype=torch.float32, device=J.device) if want_v else None
+    with torch.cuda.device(J.device):
+        check(_lib.load().sr_svals3x3_f32(_p(J), _p(S), _p(V), n, _stream()), "svals3x3")
+    return S, V
+
+
+def svals3x3_backward(J, S, V, gS):
+    _need_cuda(J, S, V, gS)
+    n = J.shape[0]
+    gJ = torch.empty((n, 3, 3), dtype=torch.float32, device=J.device)
+    with torch.cuda.device(J.device):
+        check(_lib.load().sr_svals3x3_bwd_f32(_p(J.contiguous()), _p(S.contiguous()), _p(V.contiguous()),
+                                              _p(gS.contiguous().float()), _p(gJ), n, _stream()), "svals3x3_bwd")
+    return gJ
+
+
 # ------------------------------------------------------------------------------------------------
 # Marching cubes (MCGpu/MCGpu.cpp:20-56)
 # ------------------------------------------------------------------------------------------------

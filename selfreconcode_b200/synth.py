@@ -209,17 +209,66 @@ MC_LADDER_129 = [(17, 17, 17), (33, 33, 33), (65, 65, 65), (129, 129, 129)]
 
 
 class Conf(dict):
-    """Tiny stand-in for the pyhocon ConfigTree the reference passes around (config.conf
-    `loss_*` blocks): get_float / get_int / get_bool plus `in`."""
+    """Tiny stand-in for the pyhocon ConfigTree the reference passes around (config.conf): nested dicts
+    addressed with dotted keys, get_float / get_int / get_bool / get_string / get_list / get_config,
+    and `in` with dotted keys."""
+
+    def _find(self, key):
+        cur = self
+        for part in key.split('.'):
+            if not isinstance(cur, dict) or not dict.__contains__(cur, part):
+                raise KeyError(key)
+            cur = dict.__getitem__(cur, part)
+        return cur
+
+    def __contains__(self, key):
+        try:
+            self._find(key)
+            return True
+        except KeyError:
+            return False
+
+    def __getitem__(self, key):
+        v = self._find(key)
+        return Conf(v) if isinstance(v, dict) and not isinstance(v, Conf) else v
 
     def get_float(self, k):
-        return float(self[k])
+        return float(self._find(k))
 
     def get_int(self, k):
-        return int(self[k])
+        return int(self._find(k))
 
     def get_bool(self, k):
-        return bool(self[k])
+        return bool(self._find(k))
+
+    def get_string(self, k):
+        return str(self._find(k))
+
+    def get_list(self, k):
+        return list(self._find(k))
+
+    def get_config(self, k):
+        return Conf(self._find(k))
+
+
+def reference_config(**overrides):
+    """The keys of the reference's config.conf the hot path reads, with its default values
+    (config.conf:1-120): train schedule, three loss blocks, network hyper-parameters."""
+    loss = dict(color_weight=0.5, grad_weight=0.1, normal_weight=0.1, weighted_normal=True, offset_weight=0.,
+                def_regu=dict(weight=2., c=0.5), dct_weight=0.01, sample_pix_num=2048,
+                pc_weight=dict(weight=60., mask_weight=1., laplacian_weight=0.1, edge_weight=0., norm_weight=0.01,
+                               def_consistent=dict(weight=0.1, c=0.005)))
+    level = lambda bs, r, ri: dict(start_epoch=-1, point_render=dict(radius=r, remesh_intersect=ri, batch_size=bs))
+    cfg = dict(train=dict(initial_iters=1200, skinner_pose_type=1, learning_rate=1e-4, nepoch=100, sample_pix_num=2048,
+                          opt_pose=True, opt_trans=True, opt_camera=False,
+                          scheduler=dict(milestones=[60, 80], factor=0.333),
+                          coarse=level(3, 0.006, 30), medium=level(2, 0.003, 60), fine=level(1, 0.002, 90)),
+               loss_coarse=loss, loss_medium=dict(loss), loss_fine=dict(loss),
+               sdf_net=dict(multires=6), mlp_deformer=dict(type='MLPTranslator', condlen=128, multires=6),
+               render_net=dict(type='RenderingNetwork_view_norm', condlen=256, multires_p=0, multires_x=0,
+                               multires_n=0, multires_v=4))
+    cfg.update(overrides)
+    return Conf(cfg)
 
 
 class SyntheticDataset(torch.nn.Module):
@@ -239,6 +288,23 @@ class SyntheticDataset(torch.nn.Module):
         self.pps = torch.nn.Parameter(cam["pp"].view(1, 2), requires_grad=learn_camera)
         self.register_buffer("Rs", cam["R"].view(1, 3, 3))
         self.Ts = torch.nn.Parameter(cam["T"].view(1, 3), requires_grad=learn_camera)
+        self.frame_num = n_frames
+        self.video_segmented_index = []
+
+    # ---- the rest of the surface utils.save_model / load_model / getOptNet touch (dataset/dataset.py:26-237)
+    @property
+    def camera_params(self):
+        quat = torch.tensor([0., 0., 0., 1.])       # quat2mat((0,0,0,1)) = diag(-1,-1,1)
+        return {'focal_length': self.focals.view(2), 'princeple_points': self.pps.view(2),
+                'cam2world_coord_quat': quat, 'world2cam_coord_trans': self.Ts.view(3)}
+
+    def get_batchframe_data(self, name, fids, batchsize):
+        """A window of `batchsize` consecutive frames around each id, clamped to the sequence
+        (dataset/dataset.py:128-147, single-video branch)."""
+        data = getattr(self, name)[:self.frame_num].to(fids.device)
+        starts = (fids - batchsize // 2).clamp(min=0, max=max(self.frame_num - batchsize, 0))
+        idx = starts.view(-1, 1) + torch.arange(0, batchsize, device=fids.device).view(1, batchsize)
+        return data[idx], fids - starts
 
     def get_grad_parameters(self, frame_ids, device):
         return (self.poses[frame_ids].to(device), self.trans[frame_ids].to(device),
