@@ -233,8 +233,9 @@ def cpu_reference_sample(n_rays, threads, seed=0, with_mc=True, rays=None, keep=
     bi = rays["batch_inds"]
     ang_thr = synth.ang_threshold(cam, 0.5)
     t0 = time.perf_counter()
+    sens = {"eps_f": 4e-5, "eps_a": 1e-3} if keep else None     # the tensor-core engine's error bounds (ops.TC_EPS_*)
     pts, conv, _ = O.optimize_surface_ps(cam["cam_pos"], rays["rays"], rays["init_pts"], bi, sdf_fn, def_fn,
-                                         5e-5, ang_thr, 3.05, 1.0, 10)
+                                         5e-5, ang_thr, 3.05, 1.0, 10, sensitivity=sens)
     s, g, feat = O.sdf_value_and_grad(sp, pts, 6, 1.0)
     nx = g / g.norm(dim=1, keepdim=True)
     cr, ds, J, ok = O.cardinal_rays(lambda p: def_fn(p, bi), pts, rays["rays"])
@@ -245,7 +246,7 @@ def cpu_reference_sample(n_rays, threads, seed=0, with_mc=True, rays=None, keep=
     if keep:
         u = ds - cam["cam_pos"].view(1, 3)
         ang = torch.asin(torch.linalg.cross(u, rays["rays"]).norm(dim=1) / u.norm(dim=1)) * 180.0 / np.pi
-        out["keep"] = dict(pts=pts, conv=conv, rgb=rgb, f=s, ang=ang, ang_thr=ang_thr)
+        out["keep"] = dict(pts=pts, conv=conv, rgb=rgb, f=s, ang=ang, ang_thr=ang_thr, sensitive=sens["sensitive"])
     if with_mc:
         from oracle import c_api
         t0 = time.perf_counter()
@@ -263,43 +264,58 @@ def cpu_reference_sample(n_rays, threads, seed=0, with_mc=True, rays=None, keep=
     return out
 
 
-def parity_report(gpu, cpu, dthr=5e-5, f_band=1e-5, a_band=5e-4):
-    """GPU arm vs the oracle on the SAME inputs at the benchmark's own sizes (BASELINE config[1]):
-    counts only, printed in the JSON line and asserted by tests/test_gpu_baseline_parity.py.
-      points   : elementwise |a-b| <= 1e-4*|b| + 1e-4*mean|b|
-      mask     : convergence mismatches, and how many of them are NOT borderline in the oracle's own final
-                 state (| |f| - dthr | < f_band or | angle - athr | < a_band)
-      grid     : queried-voxel sets, sign pattern of the whole 257^3 grid, marching-cubes faces (bit-exact
-                 vertex indices) and vertex positions."""
+def parity_report(gpu, cpu, band=1e-5):
+    """GPU arm vs the oracle on the SAME inputs at the benchmark's own sizes (BASELINE config[1]); counts only,
+    printed in the JSON line and asserted by tests/test_gpu_round2.py.
+
+    Rays.  OptimizeSurfacePs is a decision-driven iteration (sign(f) in the loss gradient, two threshold tests):
+    a ray whose reference trajectory comes within the engine's error bound of a decision may legitimately take
+    another branch, after which its points are unrelated.  The oracle marks those rays (`sensitive`, see
+    oracle.optimize_surface_ps); the bar applies to all the others: identical convergence mask, points and colours
+    elementwise |a-b| <= 1e-4*|b| + 1e-4*mean|b|.  The same figures over ALL rays are reported beside them.
+    Grid.  Queried-voxel sets, sign pattern and MC mesh; a sign may only differ where the oracle's own value is inside
+    fp32 evaluation noise (|f| < band): two correct fp32 evaluations of an 8x512 MLP differ there."""
     rep = {}
     pg, pc = gpu["pts"].double().cpu().numpy(), cpu["pts"].double().numpy()
-    tol = 1e-4 * np.abs(pc) + 1e-4 * np.abs(pc).mean()
-    rep["rays"] = int(pc.shape[0])
-    rep["pts_max_abs_err"] = float(np.abs(pg - pc).max())
-    rep["pts_elems_over_1e-4_rel"] = int((np.abs(pg - pc) > tol).sum())
-    cg, cc = gpu["conv"].cpu().numpy().astype(bool), cpu["conv"].numpy().astype(bool)
-    mm = cg != cc
-    f, ang = np.abs(cpu["f"].numpy()), cpu["ang"].numpy()
-    border = (np.abs(f - dthr) < f_band) | (np.abs(ang - cpu["ang_thr"]) < a_band)
-    rep["converged_gpu"], rep["converged_oracle"] = int(cg.sum()), int(cc.sum())
-    rep["conv_mismatch"] = int(mm.sum())
-    rep["conv_mismatch_not_borderline"] = int((mm & ~border).sum())
     rg, rc = gpu["rgb"].double().cpu().numpy(), cpu["rgb"].double().numpy()
-    rep["rgb_max_abs_err"] = float(np.abs(rg - rc).max())
-    rep["rgb_elems_over_1e-4_rel"] = int((np.abs(rg - rc) > 1e-4 * np.abs(rc) + 1e-4 * np.abs(rc).mean()).sum())
+    cg, cc = gpu["conv"].cpu().numpy().astype(bool), cpu["conv"].numpy().astype(bool)
+    sens = cpu["sensitive"].numpy().astype(bool)
+    ok = ~sens
+    tol_p = 1e-4 * np.abs(pc) + 1e-4 * np.abs(pc).mean()
+    tol_c = 1e-4 * np.abs(rc) + 1e-4 * np.abs(rc).mean()
+    bad_p = (np.abs(pg - pc) > tol_p).any(1)
+    bad_c = (np.abs(rg - rc) > tol_c).any(1)
+    rep["rays"] = int(pc.shape[0])
+    rep["rays_decision_sensitive"] = int(sens.sum())
+    rep["converged_gpu"], rep["converged_oracle"] = int(cg.sum()), int(cc.sum())
+    rep["conv_mismatch_all"] = int((cg != cc).sum())
+    rep["conv_mismatch_insensitive"] = int(((cg != cc) & ok).sum())
+    rep["pts_rays_over_tol_all"] = int(bad_p.sum())
+    rep["pts_rays_over_tol_insensitive"] = int((bad_p & ok).sum())
+    rep["pts_max_abs_err_insensitive"] = float(np.abs(pg - pc)[ok].max()) if ok.any() else 0.0
+    both = cg & cc
+    rep["pts_max_abs_err_converged_in_both"] = float(np.abs(pg - pc)[both].max()) if both.any() else 0.0
+    rep["rgb_rays_over_tol_insensitive"] = int((bad_c & ok).sum())
+    rep["rgb_max_abs_err_insensitive"] = float(np.abs(rg - rc)[ok].max()) if ok.any() else 0.0
     if "grid" in cpu and "grid" in gpu:
         gg, gc = gpu["grid"].cpu().numpy(), cpu["grid"].numpy()
         qg, qc = gpu["calc"].cpu().numpy().astype(bool), cpu["calc"].numpy().astype(bool)
         rep["queried_gpu"], rep["queried_oracle"] = int(qg.sum()), int(qc.sum())
         rep["queried_set_mismatch"] = int((qg != qc).sum())
-        rep["sign_mismatch"] = int(((gg > 0.0) != (gc > 0.0)).sum())
-        rep["grid_max_abs_err"] = float(np.abs(gg.astype(np.float64) - gc).max())
+        sm = (gg > 0.0) != (gc > 0.0)
+        rep["sign_mismatch"] = int(sm.sum())
+        rep["sign_mismatch_outside_fp32_band"] = int((sm & (np.abs(gc) >= band)).sum())
+        qb = qg & qc
+        rep["queried_value_max_abs_err"] = float(np.abs(gg.astype(np.float64) - gc)[qb].max())
         fg, fc = gpu["faces"].cpu().numpy(), cpu["faces"]
         rep["mc_faces_gpu"], rep["mc_faces_oracle"] = int(fg.shape[0]), int(fc.shape[0])
-        rep["mc_faces_identical"] = bool(fg.shape == fc.shape and np.array_equal(fg, fc))
-        vg, vc = gpu["verts"].cpu().numpy(), cpu["verts"]
-        rep["mc_verts_gpu"], rep["mc_verts_oracle"] = int(vg.shape[0]), int(vc.shape[0])
-        rep["mc_verts_max_abs_err"] = float(np.abs(vg - vc).max()) if vg.shape == vc.shape else None
+        rep["mc_verts_gpu"], rep["mc_verts_oracle"] = int(gpu["verts"].shape[0]), int(cpu["verts"].shape[0])
+        rep["mc_mesh_identical"] = bool(fg.shape == fc.shape and np.array_equal(fg, fc))
+        if "verts_on_oracle_grid" in gpu:     # the product's MC run on the ORACLE's grid: integer parity proper
+            v2, f2 = gpu["verts_on_oracle_grid"].cpu().numpy(), gpu["faces_on_oracle_grid"].cpu().numpy()
+            rep["mc_on_oracle_grid_faces_identical"] = bool(f2.shape == fc.shape and np.array_equal(f2, fc))
+            rep["mc_on_oracle_grid_verts_identical"] = bool(v2.shape == cpu["verts"].shape and
+                                                            np.array_equal(v2, cpu["verts"]))
     return rep
 
 
@@ -559,8 +575,13 @@ def main():
         # parity at the benchmark's own size: the GPU results of one more (untimed) step vs the oracle's
         pts_g, conv_g, rgb_g = ray_part(sc, rays_d, init_d, bi_d)
         grid_g, v_g, f_g = mc_part(sc, eng)
+        import MCGpu
+        og = cb["keep"]["grid"].to(dev)
+        v_o, f_o = MCGpu.mc_gpu(og.permute(2, 1, 0).contiguous(), eng.spacing_x, eng.spacing_y, eng.spacing_z,
+                                eng.bx, eng.by, eng.bz, 0.0)
         line["parity"] = parity_report(dict(pts=pts_g, conv=conv_g, rgb=rgb_g, grid=grid_g[0, 0],
-                                            calc=eng.last_calculated, verts=v_g, faces=f_g), cb["keep"])
+                                            calc=eng.last_calculated, verts=v_g, faces=f_g,
+                                            verts_on_oracle_grid=v_o, faces_on_oracle_grid=f_o), cb["keep"])
         line["cpu_baseline"] = {"value": cb["rays_per_sec"], "unit": "rays/s", "cores": threads, "kind": "port",
                                 "sample": "all rays of the same frame (trace times=10 + shading) and the same 257^3 "
                                           "coarse-to-fine grid + MC through oracle/ (torch fp32 CPU + C)",

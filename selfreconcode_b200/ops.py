@@ -28,6 +28,10 @@ TC_MIN_POINTS = int(_os.environ.get("SELFRECON_B200_TC_MIN_POINTS", "16384"))
 TC_EPS_F = float(_os.environ.get("SELFRECON_B200_TC_EPS_F", "4e-5"))
 TC_EPS_A = float(_os.environ.get("SELFRECON_B200_TC_EPS_A", "1e-3"))
 TC_REFINE = _os.environ.get("SELFRECON_B200_TC_REFINE", "1") != "0"
+# The tracer's in-loop fp32 re-test costs one latency-bound FFMA launch per iteration (~1.2 ms each at the bench
+# size) and cannot remove the dominant source of per-ray divergence (sign(f) in the update when |f| is below the
+# engine's error): off by default, kept for experiments.
+TC_REFINE_TRACE = _os.environ.get("SELFRECON_B200_TC_REFINE_TRACE", "0") != "0"
 
 import itertools as _it
 _uid_counter = _it.count()
@@ -910,7 +914,7 @@ def _tc_trace_body(lib, G, sdf_net, def_net, ts, td, tp, P, times, condlen, has_
     conv.zero_()
     counters.zero_()
     counters[0:1].fill_(P)
-    refine = TC_REFINE
+    refine = TC_REFINE_TRACE
     if refine:
         G.recheck_counts.zero_()
     dref = C.byref(def_net.desc) if def_net is not None else None
@@ -987,7 +991,7 @@ def trace_surface_points_tc(sdf_net, def_net, lbs, cam_pos, rays, init_pts, batc
            lbs.ws_cl.data_ptr() if lbs is not None else 0, cp, float(dthreshold), float(athreshold),
            float(w1), float(w2), tuple(ds.pe_w[i] for i in range(ds.multires)),
            tuple(dd.pe_w[i] for i in range(dd.multires)) if dd is not None else (),
-           TC_REFINE, TC_EPS_F, TC_EPS_A)
+           TC_REFINE_TRACE, TC_EPS_F, TC_EPS_A)
     G = _tc_trace_ctx.get(key)
     if G is None:
         if len(_tc_trace_ctx) >= 4:

@@ -14,7 +14,7 @@ import torch
 
 from helpers import (RATIO, SMPL_PARENTS, build_render, build_sdf_full, build_sdf_small,
                      build_skinner, build_translator, dropin, golden, mc_tri_table, plain_params,
-                     rel_err, sdf_params, wn_params)
+                     norm_err, rel_err, sdf_params, wn_params)
 
 pytestmark = pytest.mark.gpu
 FP_TOL = 1e-4
@@ -601,8 +601,8 @@ def test_tc_linear_split_bf16_matches_fp64(cuda_dev):
         W = ops.tc_pack_weights(w)
         ref = (x.double() @ w.double().t() + b.double())
         _, out, _ = ops.tc_linear(A, W, b, M, N, K, N, SR_ACT_NONE, want_out=True)
-        err = rel_err(out.cpu().numpy(), ref.cpu().numpy())
-        f32 = rel_err((x @ w.t() + b).cpu().numpy(), ref.cpu().numpy())
+        err = norm_err(out.cpu().numpy(), ref.cpu().numpy())
+        f32 = norm_err((x @ w.t() + b).cpu().numpy(), ref.cpu().numpy())
         assert err < 1e-5, (M, K, N, err, f32)   # fp32-class accuracy (fp32 itself: ~1e-6) from six bf16 products
         # chained: hidden layer (softplus) written in the tiled layout, consumed by a second layer
         w2 = (torch.randn(3, N, generator=g) / N ** 0.5).to(cuda_dev)
@@ -612,7 +612,7 @@ def test_tc_linear_split_bf16_matches_fp64(cuda_dev):
                                    want_out=True)
         h = torch.nn.functional.softplus(ref, beta=100)
         ref2 = h @ w2.double().t()
-        assert rel_err(out2.cpu().numpy(), ref2.cpu().numpy()) < 1e-5
+        assert norm_err(out2.cpu().numpy(), ref2.cpu().numpy()) < 1e-5
     # forward-mode tangent rows (4 rows per point: value, d/dx, d/dy, d/dz)
     P, K, N = 64, 64, 256
     x = torch.randn(P * 4, K, generator=g).to(cuda_dev)
@@ -623,7 +623,7 @@ def test_tc_linear_split_bf16_matches_fp64(cuda_dev):
     z = (x.double() @ w.double().t()).view(P, 4, N)
     zv = z[:, 0] + b.double()
     exp = torch.cat([torch.relu(zv)[:, None], (zv > 0).double()[:, None] * z[:, 1:]], 1).view(P * 4, N)
-    assert rel_err(out.cpu().numpy(), exp.cpu().numpy()) < 1e-5
+    assert norm_err(out.cpu().numpy(), exp.cpu().numpy()) < 1e-5
 
 
 def test_tc_mlp_matches_ffma_engine_and_golden(cuda_dev):
