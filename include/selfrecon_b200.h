@@ -299,6 +299,22 @@ int sr_tc_linear(const void* A, const void* W, const float* bias, int64_t M, int
                  int out_col0, int out_n, float* dstash, const void* mul_tiles, int mul_K, int mul_act,
                  float mul_scale, const int32_t* m_dev, cudaStream_t s);
 
+/* Training half of the tensor-core engine (model/network.py:599-639, 774-796: loss.backward() and the parameter
+ * VJPs of the implicit differentiation).  sr_tc_linear with mul_tiles != NULL is the reverse sweep of one layer; with
+ * ch == 4 it propagates the cotangents of forward-mode rows (value + 3 tangents per point), i.e. second order.
+ *   sr_tc_wgrad   dW[N x K] (row-major, ld) = delta^T x over M rows; delta / x = tiled split-bf16 activations with
+ *                 Kd / Kx feature columns (Kd padded to a multiple of 128 by the caller); `part` = scratch of
+ *                 sr_tc_wgrad_partial_bytes(M, Kd, Kx, NULL) bytes.  tcgen05 with MN-major operands: no transposes.
+ *   sr_tc_colsum  partial[slice][k] = sum over rows with row % ch == 0 (value rows) of the tiled activations: the
+ *                 bias gradient after a sum over slices.
+ *   sr_tc_unpack_rows   tiled split-bf16 -> fp32 [M][K] (inverse of sr_tc_pack_rows).                           */
+int64_t sr_tc_wgrad_partial_bytes(int64_t M, int Kd, int Kx, int* splits_out);
+void sr_tc_debug_wgrad_desc_swap(int v);   /* test knob: 1 swaps the LBO / SBO descriptor fields */
+int sr_tc_wgrad(const void* D, int Kd, const void* X, int Kx, int64_t M, float* part, float* dW, int N, int K,
+                int ld, cudaStream_t s);
+int sr_tc_colsum(const void* T, int64_t M, int K, int ch, float* partial, int slices, cudaStream_t s);
+int sr_tc_unpack_rows(const void* T, int64_t M, int K, int Kpad, float* out, int ld, cudaStream_t s);
+
 /* Batched 3x3 singular values (descending) + right singular vectors (columns of V, may be NULL), and the
  * backward of a function of the VALUES: gJ = sum_i gS_i u_i v_i^T.  Replaces `torch.svd(Jacobs.cpu())` of the
  * def_regu block (model/network.py:573-575).  J, V, gJ: [n,3,3] row-major; S, gS: [n,3]. */

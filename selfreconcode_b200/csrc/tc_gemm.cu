@@ -24,100 +24,11 @@
 //   * 4-stage shared-memory ring (48 KB per stage), two 256-column fp32 accumulators in TMEM so
 //     the epilogue of tile i overlaps the MMAs of tile i+1.
 // The FFMA engine (mlp_kernels.cu) stays the accuracy reference; tests compare both.
-#include <cuda_bf16.h>
 #include <cstdlib>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace sr_tc {
-
-#ifndef SR_TC_PLANES
-#define SR_TC_PLANES 2
-#endif
-constexpr int kPlanes = SR_TC_PLANES;
-constexpr int BM = 128, BN = 256, BK = 32, STAGES = kPlanes == 2 ? 4 : 3;
-constexpr int kEpiWarps = 8;               // two per TMEM lane quarter, each takes half the columns
-constexpr int kThreads = 64 + 32 * kEpiWarps;
-constexpr int A_PLANE = BM * BK;          // elements
-constexpr int W_PLANE = BN * BK;
-constexpr int A_STAGE = kPlanes * A_PLANE;   // 2 planes: 16 KB
-constexpr int W_STAGE = kPlanes * W_PLANE;   // 2 planes: 32 KB
-constexpr uint32_t A_STAGE_BYTES = A_STAGE * 2, W_STAGE_BYTES = W_STAGE * 2;
-constexpr size_t kSmem = (size_t)STAGES * (A_STAGE_BYTES + W_STAGE_BYTES) + 256;
-
-// ---- tiled ("pre-swizzled") global layouts ----------------------------------------------------
-// A: [row tile mt][k chunk kc][plane p][k8 (4)][row group (16)][row (8)][elem (8)]
-// W: [col tile nt][k chunk kc][plane p][k8 (4)][row group (32)][row (8)][elem (8)]
-__host__ __device__ inline size_t a_tile_off(long long mt, int kc, int KC, int p) {
-  return (((size_t)mt * KC + kc) * kPlanes + p) * A_PLANE;
-}
-__host__ __device__ inline size_t w_tile_off(int nt, int kc, int KC, int p) {
-  return (((size_t)nt * KC + kc) * kPlanes + p) * W_PLANE;
-}
-__device__ __forceinline__ int in_tile_off(int rows_per_tile, int r, int k) {
-  return (k >> 3) * (rows_per_tile * 8) + (r >> 3) * 64 + (r & 7) * 8 + (k & 7);
-}
-
-__device__ __forceinline__ void split3(float x, __nv_bfloat16& b1, __nv_bfloat16& b2, __nv_bfloat16& b3) {
-  b1 = __float2bfloat16_rn(x);
-  const float r1 = x - __bfloat162float(b1);
-  b2 = __float2bfloat16_rn(r1);
-  const float r2 = r1 - __bfloat162float(b2);
-  b3 = __float2bfloat16_rn(r2);
-}
-
-// ---- tcgen05 wrappers ------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  // cute::UMMA::SmemDescriptor: start[0,14) lbo[16,30) sbo[32,46) version[46,48)=1, swizzle none
-  uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=256
-constexpr uint32_t kIdescBase = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BM >> 4) << 24);
-
-__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                         uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   sr_smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-#define SR_TMEM_REGS32(v)                                                                          \
-  "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),  \
-  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),          \
-  "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),        \
-  "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),        \
-  "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-#define SR_TMEM_REGS32_RW(v)                                                                       \
-  "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),  \
-  "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]),          \
-  "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]),        \
-  "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]),        \
-  "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
-// asynchronous TMEM -> register load of 32 columns (this warp's 32 lanes); pair with tmem_wait
-__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      : SR_TMEM_REGS32(v)
-      : "r"(taddr));
-}
-// the registers are in/out operands so that no consumer can be scheduled above the wait
-__device__ __forceinline__ void tmem_wait(uint32_t (&v)[32]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" : SR_TMEM_REGS32_RW(v)::"memory");
-}
 
 struct LayerArgs {
   const __nv_bfloat16* A;   // tiled activations  [MT][KC][3][128x32]
@@ -257,12 +168,37 @@ __device__ __forceinline__ void epi_chunk(const LayerArgs& a, const EpiRow& r, u
           const uint32_t h0 = w0[e >> 1], h1 = w1[e >> 1];
           const float as = (e & 1) ? __uint_as_float(h0 & 0xffff0000u) + __uint_as_float(h1 & 0xffff0000u)
                                    : __uint_as_float(h0 << 16) + __uint_as_float(h1 << 16);
-          float d;
-          if constexpr (ACT == SR_ACT_SOFTPLUS100) d = 1.0f - fast_ex2(kk * as);
-          else if constexpr (ACT == SR_ACT_RELU) d = as > 0.f ? 1.f : 0.f;
-          else d = 1.f;
           float val = __uint_as_float(v[j]);
-          if (c0 + j < a.n) val = r.row_ok ? val * d : 0.f;
+          if constexpr (CH == 1) {
+            float d;
+            if constexpr (ACT == SR_ACT_SOFTPLUS100) d = 1.0f - fast_ex2(kk * as);
+            else if constexpr (ACT == SR_ACT_RELU) d = as > 0.f ? 1.f : 0.f;
+            else d = 1.f;
+            if (c0 + j < a.n) val = r.row_ok ? val * d : 0.f;
+          } else {
+            // Reverse sweep over forward-mode rows (value + 3 tangents per point; training: the cotangents of
+            // f AND of grad f / of the offset AND of its Jacobian travel together).  With a = act(z) the stored
+            // value-row activation and t_c = act'(z) u_c the stored tangent rows:
+            //   tangent rows:  u_bar_c = act'(z) t_bar_c
+            //   value row   :  z_bar   = act'(z) a_bar + act''(z) sum_c t_bar_c u_c
+            // and act'' u_c = 100 (1 - act') t_c for softplus(beta = 100), 0 for ReLU -- no division by act'.
+            const float av = __shfl_sync(0xffffffffu, as, r.lane & ~3);   // the point's value-row activation
+            float d;
+            if constexpr (ACT == SR_ACT_SOFTPLUS100) d = 1.0f - fast_ex2(kk * av);
+            else if constexpr (ACT == SR_ACT_RELU) d = av > 0.f ? 1.f : 0.f;
+            else d = 1.f;
+            float cross = 0.f;
+            if constexpr (ACT == SR_ACT_SOFTPLUS100) {
+              const float prod = r.is_val ? 0.f : val * (as * a.mul_inv_scale);    // t_bar_c * t_c
+              cross = __shfl_down_sync(0xffffffffu, prod, 1) + __shfl_down_sync(0xffffffffu, prod, 2) +
+                      __shfl_down_sync(0xffffffffu, prod, 3);
+            }
+            if (c0 + j < a.n) {
+              float o4 = val * d;
+              if constexpr (ACT == SR_ACT_SOFTPLUS100) { if (r.is_val) o4 += 100.0f * (1.0f - d) * cross; }
+              val = r.row_ok ? o4 : 0.f;
+            }
+          }
           o[j] = val * a.scale;
         }
       }
@@ -953,7 +889,7 @@ int sr_tc_linear(const void* A, const void* W, const float* bias, int64_t M, int
   a.out = out; a.out_ld = out_ld; a.dstash = dstash; a.out_col0 = out_col0; a.out_n = out_n;
   a.mul_tiles = (const __nv_bfloat16*)mul_tiles; a.mul_KC = (mul_K + 31) / 32;
   a.mul_inv_scale = mul_scale != 0.f ? 1.0f / mul_scale : 1.0f; a.m_dev = m_dev;
-  if (mul_tiles && (ch != 1 || mul_K < n_valid)) return SR_EINVAL;
+  if (mul_tiles && mul_K < n_valid) return SR_EINVAL;
   using Kern = void (*)(const LayerArgs);
   static const int use_pair = [] { const char* e = getenv("SELFRECON_B200_TC_PAIR"); return e ? atoi(e) : 1; }();
   // the pair kernel always issues N = 256 MMAs (a narrower N would take columns from BOTH halves)
@@ -961,7 +897,13 @@ int sr_tc_linear(const void* A, const void* W, const float* bias, int64_t M, int
 #define SR_TC_PICK(ACT_, CH_, MUL_) \
   (pair ? (Kern)tc_layer_pair_kernel<ACT_, CH_, MUL_> : (Kern)tc_layer_kernel<ACT_, CH_, MUL_>)
   Kern kern = nullptr;
-  if (mul_tiles) {
+  if (mul_tiles && ch == 4) {
+    switch (mul_act) {
+      case SR_ACT_NONE: kern = SR_TC_PICK(SR_ACT_NONE, 4, true); break;
+      case SR_ACT_SOFTPLUS100: kern = SR_TC_PICK(SR_ACT_SOFTPLUS100, 4, true); break;
+      case SR_ACT_RELU: kern = SR_TC_PICK(SR_ACT_RELU, 4, true); break;
+    }
+  } else if (mul_tiles) {
     switch (mul_act) {
       case SR_ACT_NONE: kern = SR_TC_PICK(SR_ACT_NONE, 1, true); break;
       case SR_ACT_SOFTPLUS100: kern = SR_TC_PICK(SR_ACT_SOFTPLUS100, 1, true); break;
@@ -1000,6 +942,7 @@ int sr_tc_linear(const void* A, const void* W, const float* bias, int64_t M, int
     if (e2 != cudaSuccess) return (int)e2;                                                                 \
   }
     SR_TC_BOTH(SR_ACT_NONE, 1, true) SR_TC_BOTH(SR_ACT_SOFTPLUS100, 1, true) SR_TC_BOTH(SR_ACT_RELU, 1, true)
+    SR_TC_BOTH(SR_ACT_NONE, 4, true) SR_TC_BOTH(SR_ACT_SOFTPLUS100, 4, true) SR_TC_BOTH(SR_ACT_RELU, 4, true)
     SR_TC_BOTH(SR_ACT_NONE, 1, false) SR_TC_BOTH(SR_ACT_SOFTPLUS100, 1, false) SR_TC_BOTH(SR_ACT_RELU, 1, false)
     SR_TC_BOTH(SR_ACT_TANH, 1, false) SR_TC_BOTH(SR_ACT_NONE, 4, false) SR_TC_BOTH(SR_ACT_SOFTPLUS100, 4, false)
     SR_TC_BOTH(SR_ACT_RELU, 4, false) SR_TC_BOTH(SR_ACT_TANH, 4, false)

@@ -34,16 +34,17 @@ class RectifiedPerspectiveCameras:
         rays = torch.stack([-ps[:, 0] / f[0] + ps[:, 2] * c[0] / f[0],
                             -ps[:, 1] / f[1] + ps[:, 2] * c[1] / f[1], ps[:, 2]], dim=1)
         rays = rays / torch.norm(rays, p=2, dim=1, keepdim=True)
-        return rays.matmul(self.R[cam_id].transpose(0, 1))
+        # rays R^T as a broadcast multiply + sum: stays differentiable w.r.t. R, launches no GEMM
+        return (rays.unsqueeze(1) * self.R[cam_id].unsqueeze(0)).sum(2)
 
     def project(self, ps, cam_id=0):
-        ps = ps.matmul(self.R[cam_id]) + self.T[cam_id].view(1, 3)
+        ps = (ps.unsqueeze(2) * self.R[cam_id].unsqueeze(0)).sum(1) + self.T[cam_id].view(1, 3)
         x = self.principal_point[cam_id, 0] - ps[:, 0] * self.focal_length[cam_id, 0] / ps[:, 2]
         y = self.principal_point[cam_id, 1] - ps[:, 1] * self.focal_length[cam_id, 1] / ps[:, 2]
         return torch.cat([x.view(-1, 1), y.view(-1, 1)], dim=1)
 
     def cam_pos(self, cam_id=0):
-        return -self.R[cam_id].matmul(self.T[cam_id].view(-1, 1)).view(-1)
+        return -(self.R[cam_id] * self.T[cam_id].view(1, 3)).sum(1)
 
     def angThreshold(self, pixoffset=0.4, cam_id=0):
         H = self.image_size[cam_id, 1].item()

@@ -19,6 +19,11 @@ from .Embedder import get_embedder
 from ._fused import FoldCache, needs_autograd, ratio_value, require_cuda, SR_ACT_NONE, SR_ACT_RELU
 
 
+def _mm(a, b):
+    """small trailing-dim matmul as broadcast multiply + sum (4x4 bone transforms): elementwise kernels only."""
+    return (a.unsqueeze(-1) * b.unsqueeze(-3)).sum(-2)
+
+
 def batch_rodrigues(theta):
     """axis-angle -> rotation (reference: smpl_pytorch/util.py:35-68), differentiable."""
     angle = torch.norm(theta + 1e-8, p=2, dim=1).unsqueeze(-1)
@@ -56,6 +61,32 @@ class CompositeDeformer(nn.Module):
         for cond, deformer in zip(conds, self.defs):
             out = deformer(out, cond, batch_inds, **kwargs)
         return out
+
+    def forward_train(self, ps, conds, batch_inds, ratio, want_jac=True):
+        """Differentiable D(p) and (optionally) dD/dp on the tensor-core engine: the translator carries the
+        point as value + 3 forward tangents (so d offset / dp is an output, utils/utils.py:106-120 without the
+        three create_graph VJPs through the MLP); the LBS part and its 3x3 Jacobian go through the
+        GridSamplerMine op and its double-backward kernels.  ps [P,3] with batch_inds, or [N,V,3] (mesh mode).
+        -> (D(p) like ps, J [P,3,3] | None)"""
+        from selfreconcode_b200 import train_ops as T
+        import utils
+        tr, sk = self.defs[0], self.defs[1]
+        shape = ps.shape
+        if batch_inds is None:
+            n, v = ps.shape[0], ps.shape[1]
+            cond_rows = conds[0].view(n, 1, -1).expand(n, v, conds[0].shape[-1]).reshape(n * v, -1)
+        else:
+            cond_rows = conds[0][batch_inds]
+        pts = ps.reshape(-1, 3)
+        off, Joff = tr.forward_train(pts, cond_rows, ratio, want_jac)
+        tr.offset = off.view(shape)
+        q = pts + off
+        d = sk(q.view(shape), conds[1], batch_inds).reshape(-1, 3)
+        if not want_jac:
+            return d.view(shape), None
+        Jl = utils.compute_Jacobian(q, d, True, True)                        # dLBS/dq via the sampler's backward ops
+        eye = torch.eye(3, dtype=pts.dtype, device=pts.device).unsqueeze(0)
+        return d.view(shape), T.small_matmul(Jl, eye + Joff)
 
     def forward_fused(self, ps, conds, batch_inds, ratio, want_jac=False, want_corner_idx=False):
         """-> (D(p) [P,3], J [P,3,3] | None, lbs corner indices | None); no graph.  Also sets
@@ -119,6 +150,24 @@ class MLPTranslator(nn.Module):
         net = self._cache.get(params, build)
         net.set_pe_weights(ops.annealing_weights(self.multires, ratio_value(ratio, "deformerRatio")))
         return net
+
+    def forward_train(self, pts, cond_rows, ratio, want_jac=True):
+        """pts [P,3], cond_rows [P,C] -> (offset [P,3], d offset / d p [P,3(m),3(c)] | None), differentiable
+        w.r.t. pts, cond_rows and the parameters through the tensor-core training engine."""
+        from selfreconcode_b200 import train_ops as T
+        require_cuda(pts, "MLPTranslator.forward_train")
+        ch = 4 if want_jac else 1
+        L = self.num_layers - 1
+        Ws = [getattr(self, "lin" + str(l)).weight for l in range(L)]
+        bs = [getattr(self, "lin" + str(l)).bias for l in range(L)]
+        acts = [SR_ACT_RELU] * (L - 1) + [SR_ACT_NONE]
+        d_in = 3 + 6 * self.multires + self.feature_vector_size
+        pe_w = ops.annealing_weights(self.multires, ratio_value(ratio, "deformerRatio"))
+        x0 = T.embed_rows(pts, self.multires, pe_w, ch, extra=cond_rows)
+        out = T.tc_mlp(x0, T.MlpConfig(acts, [False] * L, d_in, ch), Ws, bs).view(pts.shape[0], ch, 3)
+        off = out[:, 0]
+        jac = out[:, 1:].transpose(1, 2) if want_jac else None      # [P, m, c] = d off_m / d p_c
+        return off, jac
 
     def forward(self, ps, conds, batch_inds=None, **kwargs):
         require_cuda(ps, "MLPTranslator.forward")
@@ -238,7 +287,7 @@ class LBSkinner(nn.Module):
         results = [make_A(R[:, 0], Js[:, 0])]
         for i in range(1, self.parents.shape[0]):
             p = int(self.parents[i])
-            results.append(torch.matmul(results[p], make_A(R[:, i], Js[:, i] - Js[:, p])))
+            results.append(_mm(results[p], make_A(R[:, i], Js[:, i] - Js[:, p])))
         return torch.stack(results, dim=1), Js
 
     def posedSkeleton(self, conds):
@@ -264,25 +313,26 @@ class LBSkinner(nn.Module):
         results, Js = self._chain(poses)
         if self.init_pose is None:
             Js_w0 = torch.cat([Js, torch.zeros(batch_size, 24, 1, 1, device=poses.device)], dim=2)
-            init_bone = F.pad(torch.matmul(results, Js_w0), [3, 0, 0, 0, 0, 0, 0, 0])
+            init_bone = F.pad(_mm(results, Js_w0), [3, 0, 0, 0, 0, 0, 0, 0])
             A = results - init_bone
         else:
-            A = torch.matmul(results, self.init_pose.view(1, 24, 4, 4).expand(batch_size, 24, 4, 4))
+            A = _mm(results, self.init_pose.view(1, 24, 4, 4).expand(batch_size, 24, 4, 4))
         nps = 2. * (tps.reshape(-1, 3) - self.b_min) / (self.b_max - self.b_min) - 1.
         ps_ws = GridSamplerMine3dFunction.apply(self.ws, nps.reshape(1, 1, 1, -1, 3)) \
             .view(-1, nps.shape[0]).transpose(0, 1)
         if batch_inds is None:
             _, pnum, _ = ps.shape
             ps_ws = ps_ws.view(batch_size, pnum, 24)
-            T = torch.matmul(ps_ws, A.view(batch_size, 24, 16)).view(batch_size, pnum, 4, 4)
+            T = (ps_ws.unsqueeze(-1) * A.view(batch_size, 1, 24, 16)).sum(2).view(batch_size, pnum, 4, 4)
             ph = torch.cat([ps, torch.ones(batch_size, pnum, 1, device=ps.device)], dim=2)
-            return torch.matmul(T, ph.unsqueeze(-1))[:, :, :3, 0] + trans.view(-1, 1, 3)
+            return (T[:, :, :3, :] * ph.unsqueeze(-2)).sum(-1) + trans.view(-1, 1, 3)
         ps = ps.reshape(-1, 3)
         assert batch_inds.numel() == ps.shape[0]
         # one gather instead of the reference's per-frame masked loop with a host sync per frame
         # (Deformer.py:226-231): T_p = sum_j w_pj A[b_p, j]
-        T = torch.einsum('pj,pjk->pk', ps_ws, A.view(batch_size, 24, 16)[batch_inds]).view(-1, 4, 4)
-        v = torch.matmul(T, F.pad(ps, (0, 1), mode='constant', value=1).unsqueeze(-1))[:, :3, 0]
+        # (broadcast multiply + sum instead of einsum / matmul: no cuBLAS launches in the training step)
+        T = (ps_ws.unsqueeze(-1) * A.view(batch_size, 24, 16)[batch_inds]).sum(1).view(-1, 4, 4)
+        v = (T[:, :3, :] * F.pad(ps, (0, 1), mode='constant', value=1).unsqueeze(-2)).sum(-1)
         return v + trans[batch_inds]
 
 

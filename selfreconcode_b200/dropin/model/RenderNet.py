@@ -61,8 +61,31 @@ class RenderingNetwork_view_norm(nn.Module):
         net.set_pe_weights(ops.annealing_weights(self.multires_v, ratio_value(ratio, "renderRatio")))
         return net
 
+    def _train_ok(self):
+        from selfreconcode_b200 import train_ops
+        return train_ops.TC_TRAIN_ENABLED and self.mode == 'idr' and self.multires_n == 0 and self.multires_v > 0
+
+    def forward_train(self, points, normals, view_dirs, feature_vectors, ratio):
+        """Differentiable colours on the tensor-core training engine (inputs and parameters)."""
+        from selfreconcode_b200 import train_ops as T
+        L = self.num_layers - 1
+        Ws, bs = [], []
+        for l in range(L):
+            lin = getattr(self, "lin" + str(l))
+            Ws.append(T.weight_norm_eff(lin.weight_v, lin.weight_g) if self.weight_norm else lin.weight)
+            bs.append(lin.bias)
+        pe_w = ops.annealing_weights(self.multires_v, ratio_value(ratio, "renderRatio"))
+        ev = T.embed_rows(view_dirs, self.multires_v, pe_w, 1, ld=3 + 6 * self.multires_v)
+        x = torch.cat([points, ev, normals, feature_vectors], dim=-1)
+        x0 = torch.nn.functional.pad(x, (0, (-x.shape[1]) % 32))
+        acts = [SR_ACT_RELU] * (L - 1) + [SR_ACT_NONE]
+        out = T.tc_mlp(x0, T.MlpConfig(acts, [False] * L, x.shape[1], 1), Ws, bs)
+        return torch.tanh(out)
+
     def forward(self, points, normals, view_dirs, feature_vectors, ratio):
         require_cuda(points, "RenderingNetwork_view_norm.forward")
+        if self._train_ok() and needs_autograd(points, normals, view_dirs, feature_vectors, *self.parameters()):
+            return self.forward_train(points, normals, view_dirs, feature_vectors, ratio)
         if not needs_autograd(points, normals, view_dirs, feature_vectors, *self.parameters()):
             return ops.render_forward(self.fused(ratio), points, normals, view_dirs, feature_vectors)
         ratio = ratio_value(ratio, 'renderRatio')

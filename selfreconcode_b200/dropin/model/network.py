@@ -118,6 +118,42 @@ class ImplicitNetwork(nn.Module):
         sdf, grad, feat = ops.sdf_forward(net, pts, want_grad, nfeat)
         return sdf.view(-1, 1), grad, feat
 
+    # ---- fused training path (tensor-core engine, forward tangents) --------------------------
+    def _train_ok(self):
+        from selfreconcode_b200 import train_ops
+        return train_ops.TC_TRAIN_ENABLED and self.multires > 0 and self.d_out == 1
+
+    def forward_train(self, input, ratio, want_grad=True, want_feat=True):
+        """Differentiable (w.r.t. the input AND the parameters) evaluation on the tensor-core engine:
+        -> (sdf [P,1], grad f [P,3] | None, feature [P,F] | None).  With want_grad the point travels as four
+        rows (value + forward tangents), so grad f is an OUTPUT of the graph: losses on it (eikonal, normals)
+        back-propagate with one reverse sweep -- the reference's create_graph=True / double backward
+        (network.py:102-114, 608) without a second-order graph."""
+        from selfreconcode_b200 import train_ops as T
+        require_cuda(input, "ImplicitNetwork.forward_train")
+        pts = input.reshape(-1, 3)
+        P = pts.shape[0]
+        ch = 4 if want_grad else 1
+        L = self.num_layers - 1
+        Ws, bs, acts, skips = [], [], [], []
+        for l in range(L):
+            lin = getattr(self, "lin" + str(l))
+            W = T.weight_norm_eff(lin.weight_v, lin.weight_g) if self.weight_norm else lin.weight
+            b = lin.bias
+            if l == L - 1 and not want_feat:      # value only: the feature head is not evaluated
+                W, b = W[:self.d_out], b[:self.d_out]
+            Ws.append(W)
+            bs.append(b)
+            acts.append(SR_ACT_SOFTPLUS100 if l < L - 1 else SR_ACT_NONE)
+            skips.append(l in self.skip_in)
+        d_in = 3 + 6 * self.multires
+        x0 = T.embed_rows(pts, self.multires, self._pe_weights(ratio_value(ratio, "sdfRatio")), ch)
+        out = T.tc_mlp(x0, T.MlpConfig(acts, skips, d_in, ch), Ws, bs).view(P, ch, -1)
+        sdf = out[:, 0, :self.d_out]
+        grad = out[:, 1:, 0] if want_grad else None
+        feat = out[:, 0, self.d_out:] if (want_feat and out.shape[2] > self.d_out) else None
+        return sdf, grad, feat
+
     # ---- reference surface ---------------------------------------------------------------
     def forward(self, input, ratio):
         require_cuda(input, "ImplicitNetwork.forward")

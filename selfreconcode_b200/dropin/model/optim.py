@@ -246,8 +246,14 @@ class OptimNetwork(nn.Module):
         base = initTmpPs if extra_points is None else torch.cat([initTmpPs, extra_points.detach()], dim=0)
         nonmnfld_pnts = utils.sample_points(base, 1.8, 0.01)
         nonmnfld_pnts.requires_grad_()
-        pred = self.sdf(nonmnfld_pnts, ratio)
-        grad = self.sdf.gradient(nonmnfld_pnts, pred)
+        fused_train = utils.train_fused(self.deformer, self.sdf) and self.netRender._train_ok() \
+            if hasattr(self.netRender, "_train_ok") else False
+        if fused_train:
+            # eikonal term on the tensor-core training engine: grad f is a forward-mode output (network.py:545-547)
+            _, grad, _ = self.sdf.forward_train(nonmnfld_pnts, ratio, want_grad=True, want_feat=False)
+        else:
+            pred = self.sdf(nonmnfld_pnts, ratio)
+            grad = self.sdf.gradient(nonmnfld_pnts, pred)
         grad_loss = ((grad.norm(2, dim=-1) - 1) ** 2).mean()
         self.info['grad_loss'] = grad_loss.item()
         total_loss = total_loss + grad_loss * conf.get_float('grad_weight')
@@ -260,11 +266,24 @@ class OptimNetwork(nn.Module):
             self.batch_inds = batch_inds[check]
             self.col_inds = col_inds[check]
             self.row_inds = row_inds[check]
-            sdfs = self.sdf(self.TmpPs, ratio)
-            nx = torch.autograd.grad(sdfs, self.TmpPs, torch.ones_like(sdfs), retain_graph=True, create_graph=True)[0]
-            nx = nx / nx.norm(dim=1, keepdim=True)
-            crays, defVs = utils.compute_cardinal_rays(self.deformer, self.TmpPs, self.rays, defconds,
-                                                       self.batch_inds, ratio, 'train')
+            grad_d_p = None
+            if fused_train:
+                # f, grad f, rendcond in one forward-mode sweep; D(p), dD/dp in another (network.py:606-610)
+                sdfs, nx, rendcond_p = self.sdf.forward_train(self.TmpPs, ratio, want_grad=True, want_feat=True)
+                self.sdf.rendcond = rendcond_p
+                nx = nx / nx.norm(dim=1, keepdim=True)
+                defVs, grad_d_p = self.deformer.forward_train(self.TmpPs, defconds, self.batch_inds, ratio, True)
+                Jinv, inv_mask = utils.FastDiff3x3MinvFunction.apply(grad_d_p)
+                crays = utils.mv3(Jinv, self.rays.view(-1, 3))
+                crays = torch.where(inv_mask.view(-1, 1), crays, self.rays.detach())
+                crays = crays / crays.norm(dim=1, keepdim=True)
+            else:
+                sdfs = self.sdf(self.TmpPs, ratio)
+                nx = torch.autograd.grad(sdfs, self.TmpPs, torch.ones_like(sdfs), retain_graph=True,
+                                         create_graph=True)[0]
+                nx = nx / nx.norm(dim=1, keepdim=True)
+                crays, defVs = utils.compute_cardinal_rays(self.deformer, self.TmpPs, self.rays, defconds,
+                                                           self.batch_inds, ratio, 'train')
             if conf.get_float('color_weight') > 0.:
                 colors = utils.compute_netRender_color(self.netRender, self.TmpPs, defVs, nx, crays, self.sdf.rendcond,
                                                        None, ratio)
@@ -281,13 +300,16 @@ class OptimNetwork(nn.Module):
                     weights = torch.ones(nx.shape[0], device=device)
                 gtn = datas['normal'].to(device)[self.batch_inds, self.row_inds, self.col_inds, :]
                 flip = torch.tensor([[-1., 0., 0.], [0., 1., 0.], [0., 0., -1.]], device=device)
-                gtn = ((cameras.R[0] @ flip) @ gtn.view(-1, 3, 1)).view(-1, 3)
+                gtn = utils.mv3((cameras.R[0] * flip.diagonal().view(1, 3)).unsqueeze(0), gtn.view(-1, 3))
                 gtnorms = gtn.norm(dim=1, keepdim=True)
                 valid = (gtnorms > 0.0001)[..., 0]
                 gtn = torch.where(valid.view(-1, 1), gtn / gtnorms.clamp(min=1e-12), gtn)
-                ds = self.deformer(self.TmpPs, defconds, self.batch_inds, ratio=ratio)
-                J = utils.compute_Jacobian(self.TmpPs, ds, True, True)
-                gtn = (J.transpose(-2, -1) @ gtn.view(-1, 3, 1)).view(-1, 3)
+                if grad_d_p is not None:
+                    J = grad_d_p               # the forward-mode Jacobian of the sweep above
+                else:
+                    ds = self.deformer(self.TmpPs, defconds, self.batch_inds, ratio=ratio)
+                    J = utils.compute_Jacobian(self.TmpPs, ds, True, True)
+                gtn = utils.mtv3(J, gtn.view(-1, 3))
                 normal_loss = (gtn - nx).norm(2, dim=1) * weights
                 normal_loss = _scatter_mean(normal_loss[valid], self.batch_inds[valid], N).mean()
                 self.info['normal_loss'] = normal_loss.item()
@@ -317,8 +339,15 @@ class OptimNetwork(nn.Module):
         if 'def_regu' in conf and conf.get_float('def_regu.weight') > 0.:
             pts = torch.cat([base, utils.sample_points(base, 1.8, 0.01, 0)], dim=0).view(1, -1, 3).expand(N, -1, 3)
             pts = pts.detach().requires_grad_()
-            dv = tr(pts, d_cond, ratio=ratio)
-            J = utils.compute_Jacobian(pts, dv, True, True)
+            if utils.train_fused(self.deformer):
+                # translator Jacobian as a forward-mode output: J = I + d offset / d p
+                n_, m_ = pts.shape[0], pts.shape[1]
+                cr = d_cond.view(n_, 1, -1).expand(n_, m_, d_cond.shape[-1]).reshape(n_ * m_, -1)
+                _, Joff = tr.forward_train(pts.reshape(-1, 3), cr, ratio, want_jac=True)
+                J = torch.eye(3, device=pts.device).unsqueeze(0) + Joff
+            else:
+                dv = tr(pts, d_cond, ratio=ratio)
+                J = utils.compute_Jacobian(pts, dv, True, True)
             sv = torch.log(utils.singular_values_3x3(J))
             dl = utils.GMRobustError((sv * sv).sum(1), conf.get_float('def_regu.c'), True).mean()
             self.info['def_loss'] = dl.item()
@@ -329,7 +358,7 @@ class OptimNetwork(nn.Module):
             bp, _ = self.dataset.get_batchframe_data('poses', frame_ids, nlen)
             bt, _ = self.dataset.get_batchframe_data('trans', frame_ids, nlen)
             pj = self.deformer.defs[1].posedSkeleton([bp.reshape(N * nlen, 24, 3), bt.reshape(N * nlen, 3)])
-            dct = self.dctnull[None, :, :].matmul(pj.reshape(N, nlen, 72)).abs().mean()
+            dct = (self.dctnull[None, :, :, None] * pj.reshape(N, 1, nlen, 72)).sum(2).abs().mean()
             self.info['dct_loss'] = dct.item()
             out = out + dct * conf.get_float('dct_weight')
         return out
@@ -542,16 +571,23 @@ class OptimNetwork(nn.Module):
             d = self.deformer(p, defconds, self.batch_inds, ratio=ratio)
             grad_d_p = utils.compute_Jacobian(p, d, False, False)
         v_cross = _cross_matrix(v.detach())
-        a1 = v_cross.matmul(grad_d_p)
+        a1 = (v_cross.unsqueeze(-1) * grad_d_p.unsqueeze(-3)).sum(-2)          # [v]x J, elementwise (no GEMM launch)
         b = torch.cat([grad_f_p.view(-1, 1, 3), a1], dim=1)           # [P,4,3]
-        btb = b.permute(0, 2, 1).matmul(b)
+        btb = (b.unsqueeze(-1) * b.unsqueeze(-2)).sum(1)
         btb_inv, check = Fast3x3Minv(btb.contiguous())
         self.info['invInfo'] = (check.numel(), check.sum().item())
-        rhs_1 = grad_l_p.view(-1, 1, 3).matmul(btb_inv.matmul(b.permute(0, 2, 1)))   # [P,1,4]
+        # rhs = dL/dp (b^T b)^-1 b^T   [P,1,4]
+        rhs_1 = utils.mv3(b, utils.mtv3(btb_inv, grad_l_p.view(-1, 3))).view(-1, 1, 4)
         loss = 0.
         # theta: VJP of the sdf with cotangent -rhs[...,0]
+        train_fused = fusable and utils.train_fused(self.deformer, self.sdf)
         params = [q for q in self.sdf.parameters() if q.requires_grad]
-        grads = torch.autograd.grad(self.sdf(p, ratio), params, -rhs_1[:, :, 0])
+        if train_fused:   # first-order VJP through the tensor-core training engine (value rows only, no feature head)
+            f_p = self.sdf.forward_train(p.detach(), ratio, want_grad=False, want_feat=False)[0]
+        else:
+            f_p = self.sdf(p, ratio)
+        grads = torch.autograd.grad(f_p, params, -rhs_1[:, :, 0], allow_unused=True)
+        grads = [g if g is not None else torch.zeros_like(q) for g, q in zip(grads, params)]
         for q, g in zip(params, grads):
             loss = loss + (q * g).sum()
         # phi, latent codes, pose: VJP of the deformer with cotangent rhs[...,1:] (-[v]x)
@@ -561,14 +597,17 @@ class OptimNetwork(nn.Module):
                 if t.requires_grad:
                     opt_defconds.append(t)
         params = [q for q in self.deformer.parameters() if q.requires_grad]
-        d = self.deformer(p, defconds, self.batch_inds, ratio=ratio)
-        temp = (rhs_1[:, :, -3:].matmul(-v_cross)).view(-1, 3)
+        if train_fused:
+            d = self.deformer.forward_train(p.detach(), defconds, self.batch_inds, ratio, want_jac=False)[0]
+        else:
+            d = self.deformer(p, defconds, self.batch_inds, ratio=ratio)
+        temp = utils.mtv3(-v_cross, rhs_1[:, 0, -3:])
         grads = torch.autograd.grad(d, params + opt_defconds, temp)
         for q, g in zip(params + opt_defconds, grads):
             loss = loss + (q * g).sum()
         if v.requires_grad:
             dc_cross = _cross_matrix(d.detach() - c.detach().view(1, 3))
-            loss = loss + (v * rhs_1[:, :, -3:].matmul(dc_cross).view(-1, 3)).sum()
+            loss = loss + (v * utils.mtv3(dc_cross, rhs_1[:, 0, -3:])).sum()
         if c.requires_grad:
             loss = loss + (c * (-temp.sum(0))).sum()
         loss.backward()

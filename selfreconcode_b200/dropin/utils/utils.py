@@ -108,12 +108,34 @@ def _fusable(deformer):
     return hasattr(deformer, "_fusable") and deformer._fusable()
 
 
+def train_fused(deformer, sdf=None):
+    """True when the training evaluations can run on the tensor-core training engine (train_ops.py)."""
+    from selfreconcode_b200 import train_ops
+    if not (train_ops.TC_TRAIN_ENABLED and _fusable(deformer) and hasattr(deformer, "forward_train")):
+        return False
+    return sdf is None or (hasattr(sdf, "_train_ok") and sdf._train_ok())
+
+
+def mv3(M, v):
+    """[P,3,3] x [P,3] without a GEMM launch."""
+    return (M * v.unsqueeze(-2)).sum(-1)
+
+
+def mtv3(M, v):
+    """[P,3,3]^T x [P,3]."""
+    return (M * v.unsqueeze(-1)).sum(-2)
+
+
 def compute_deformed_normals(sdf, deformer, ps, defconds, batch_inds, ratio, phase):
     check = phase in ('train', 'Train')
     if not check and _fusable(deformer) and hasattr(sdf, "forward_fused"):
         # no graph requested: f, grad f, D, dD/dp from the fused forward-mode kernels
         _, onx, _ = sdf.forward_fused(ps, ratio, want_grad=True, want_feat=False)
         ds, grad_d_p, _ = deformer.forward_fused(ps, defconds, batch_inds, ratio, want_jac=True)
+    elif check and train_fused(deformer, sdf):
+        # training graph on the tensor-core engine: grad f and dD/dp are forward-mode OUTPUTS
+        _, onx, _ = sdf.forward_train(ps, ratio, want_grad=True, want_feat=False)
+        ds, grad_d_p = deformer.forward_train(ps, defconds, batch_inds, ratio, want_jac=True)
     else:
         sdfs = sdf(ps, ratio)
         onx = torch.autograd.grad(sdfs, ps, torch.ones_like(sdfs), retain_graph=check,
@@ -121,13 +143,13 @@ def compute_deformed_normals(sdf, deformer, ps, defconds, batch_inds, ratio, pha
         ds = deformer(ps, defconds, batch_inds, ratio=ratio)
         grad_d_p = compute_Jacobian(ps, ds, check, check)
     grad_d_p_inv, inv_mask = FastDiff3x3MinvFunction.apply(grad_d_p)
-    nx = grad_d_p_inv.transpose(-2, -1).matmul(onx.view(-1, 3, 1)).view(-1, 3)
+    nx = mtv3(grad_d_p_inv, onx.view(-1, 3))
     n_inv_mask = ~inv_mask
     if n_inv_mask.sum().item() > 0:
         print('unwished error n_inv_mask:(%d:%d)' % (n_inv_mask.sum().item(), n_inv_mask.numel()))
         nnx = torch.zeros_like(nx)
         nnx[inv_mask] = nx[inv_mask]
-        nnx[n_inv_mask] = grad_d_p[n_inv_mask].matmul(onx[n_inv_mask].unsqueeze(-1)).view(-1, 3)
+        nnx[n_inv_mask] = mv3(grad_d_p[n_inv_mask], onx[n_inv_mask])
         nx = nnx
     nx = nx / nx.norm(dim=1, keepdim=True)
     return nx, ds
@@ -137,11 +159,13 @@ def compute_cardinal_rays(deformer, ps, rays, defconds, batch_inds, ratio, phase
     check = phase in ('train', 'Train')
     if not check and _fusable(deformer):
         ds, grad_d_p, _ = deformer.forward_fused(ps, defconds, batch_inds, ratio, want_jac=True)
+    elif check and train_fused(deformer):
+        ds, grad_d_p = deformer.forward_train(ps, defconds, batch_inds, ratio, want_jac=True)
     else:
         ds = deformer(ps, defconds, batch_inds, ratio=ratio)
         grad_d_p = compute_Jacobian(ps, ds, check, check)
     grad_d_p_inv, inv_mask = FastDiff3x3MinvFunction.apply(grad_d_p)
-    crays = grad_d_p_inv.matmul(rays.view(-1, 3, 1)).view(-1, 3)
+    crays = mv3(grad_d_p_inv, rays.view(-1, 3))
     n_inv_mask = ~inv_mask
     if n_inv_mask.sum().item() > 0:
         print('unwished error n_inv_mask:(%d:%d)' % (n_inv_mask.sum().item(), n_inv_mask.numel()))

@@ -1,0 +1,133 @@
+"""GPU: the training half of the tensor-core engine (selfreconcode_b200/train_ops.py) against plain torch
+fp64 autograd of the same computation.
+
+  * sr_tc_wgrad (MN-major tcgen05 GEMM over the tiled activations) vs delta^T x
+  * TcMlpFunction forward / backward with 1 row per point (first order) and 4 rows per point (value + 3 forward
+    tangents: the backward contains act'' -- what the reference gets from double backward), incl. the SDF's skip
+    connection and narrow first / last layers."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import norm_err
+
+pytestmark = pytest.mark.gpu
+SP, RELU, NONE = 1, 2, 0
+
+
+def _ref_forward(x0, Ws, bs, acts, skips, d_in, ch):
+    """The forward-mode MLP in differentiable torch ops (any dtype): rows = (point, channel); channel 0 carries the
+    value, channels 1..3 tangents that see act'(z_value) and no bias."""
+    M = x0.shape[0]
+    P = M // ch
+    x = x0
+    for i, (W, b, act, skip) in enumerate(zip(Ws, bs, acts, skips)):
+        if skip:
+            x = torch.cat([x[:, :W.shape[1] - d_in], x0[:, :d_in]], dim=1) / np.sqrt(2)
+        z = x[:, :W.shape[1]] @ W.t()
+        z = z.view(P, ch, -1)
+        zv = z[:, 0] + (b if b is not None else 0)
+        if act == SP:
+            a = torch.nn.functional.softplus(zv, beta=100)
+            d = torch.sigmoid(100 * zv)
+        elif act == RELU:
+            a = torch.relu(zv)
+            d = (zv > 0).to(zv.dtype)
+        else:
+            a, d = zv, torch.ones_like(zv)
+        if ch == 1:
+            x = a
+        else:
+            x = torch.cat([a.unsqueeze(1), d.unsqueeze(1) * z[:, 1:]], dim=1).reshape(M, -1)
+    return x
+
+
+def _case(dev, ch, dims, acts, skips, d_in, ld, P, seed):
+    g = torch.Generator().manual_seed(seed)
+    M = P * ch
+    x0 = torch.zeros(M, ld)
+    x0[:, :d_in] = torch.randn(M, d_in, generator=g) * 0.5
+    Ws, bs = [], []
+    k = d_in
+    for i, n in enumerate(dims):
+        kin = k if not skips[i] else k + d_in
+        Ws.append(torch.randn(n, kin, generator=g) / np.sqrt(kin) * (3.0 if acts[i] == SP else 1.4))
+        bs.append(torch.randn(n, generator=g) * 0.05)
+        k = n
+    R = torch.randn(M, dims[-1], generator=g)
+    return x0, Ws, bs, R
+
+
+@pytest.mark.parametrize("swap", [0, 1])
+def test_wgrad_matches_fp64(cuda_dev, swap):
+    from selfreconcode_b200 import _lib, ops
+    from selfreconcode_b200.train_ops import _Workspace
+    from selfreconcode_b200.ops import _p, _stream
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    res = {}
+    for (M, n, k) in ((5000, 512, 512), (777, 257, 64), (20000, 3, 512), (4100, 473, 192)):
+        d = torch.randn(M, n, generator=g)
+        x = torch.randn(M, k, generator=g)
+        Kd, Kx = (n + 127) // 128 * 128, (k + 31) // 32 * 32
+        dp = torch.zeros(M, Kd)
+        dp[:, :n] = d
+        xp = torch.zeros(M, Kx)
+        xp[:, :k] = x
+        D = ops.tc_pack_rows(dp.to(cuda_dev))
+        X = ops.tc_pack_rows(xp.to(cuda_dev))
+        part = _Workspace.get(cuda_dev, lib.sr_tc_wgrad_partial_bytes(M, Kd, Kx, None))
+        dW = torch.empty(n, k, device=cuda_dev)
+        lib.sr_tc_debug_wgrad_desc_swap(swap)
+        try:
+            rc = lib.sr_tc_wgrad(_p(D), Kd, _p(X), Kx, M, _p(part), _p(dW), n, k, k, _stream())
+        finally:
+            lib.sr_tc_debug_wgrad_desc_swap(0)
+        assert rc == 0
+        ref = d.double().t() @ x.double()
+        res[(M, n, k)] = norm_err(dW.cpu().numpy(), ref.numpy())
+    print("wgrad swap=%d errors:" % swap, res)
+    if swap == 0:
+        assert max(res.values()) < 2e-5, res
+    else:
+        assert min(res.values()) > 1e-2, "the swapped descriptor must NOT work (guards the layout reasoning)"
+
+
+CASES = {
+    "relu_ch1": dict(ch=1, dims=[512, 512, 3], acts=[RELU, RELU, NONE], skips=[False] * 3, d_in=167, ld=192, P=3001),
+    "relu_ch4": dict(ch=4, dims=[512, 512, 3], acts=[RELU, RELU, NONE], skips=[False] * 3, d_in=167, ld=192, P=700),
+    "sdf_ch4": dict(ch=4, dims=[512, 473, 512, 257], acts=[SP, SP, SP, NONE], skips=[False, False, True, False],
+                    d_in=39, ld=64, P=650),
+    "sdf_ch1": dict(ch=1, dims=[512, 473, 512, 257], acts=[SP, SP, SP, NONE], skips=[False, False, True, False],
+                    d_in=39, ld=64, P=2100),
+    "small_ch4": dict(ch=4, dims=[64, 64, 1], acts=[SP, SP, NONE], skips=[False] * 3, d_in=39, ld=64, P=300),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_tc_mlp_function_vs_autograd(cuda_dev, name):
+    from selfreconcode_b200.train_ops import MlpConfig, tc_mlp
+    c = CASES[name]
+    x0, Ws, bs, R = _case(cuda_dev, c["ch"], c["dims"], c["acts"], c["skips"], c["d_in"], c["ld"], c["P"], 11)
+    # reference: fp64 autograd
+    x0r = x0.double().requires_grad_(True)
+    Wr = [w.double().requires_grad_(True) for w in Ws]
+    br = [b.double().requires_grad_(True) for b in bs]
+    out_r = _ref_forward(x0r, Wr, br, c["acts"], c["skips"], c["d_in"], c["ch"])
+    (out_r * R.double()).sum().backward()
+    # product
+    x0g = x0.to(cuda_dev).requires_grad_(True)
+    Wg = [w.to(cuda_dev).requires_grad_(True) for w in Ws]
+    bg = [b.to(cuda_dev).requires_grad_(True) for b in bs]
+    cfg = MlpConfig(c["acts"], c["skips"], c["d_in"], c["ch"])
+    out_g = tc_mlp(x0g, cfg, Wg, bg)
+    errs = {"out": norm_err(out_g.detach().cpu().numpy(), out_r.detach().numpy())}
+    (out_g * R.to(cuda_dev)).sum().backward()
+    errs["x0"] = norm_err(x0g.grad.cpu().numpy()[:, :c["d_in"]], x0r.grad.numpy()[:, :c["d_in"]])
+    for i in range(len(Ws)):
+        errs["W%d" % i] = norm_err(Wg[i].grad.cpu().numpy(), Wr[i].grad.numpy())
+        errs["b%d" % i] = norm_err(bg[i].grad.cpu().numpy(), br[i].grad.numpy())
+    print(name, {k: "%.1e" % v for k, v in errs.items()})
+    assert errs["out"] < 1e-4
+    assert max(v for k, v in errs.items() if k != "out") < 3e-4, errs
+    assert (x0g.grad[:, c["d_in"]:] == 0).all()

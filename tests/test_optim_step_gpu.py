@@ -127,3 +127,59 @@ def test_infer_rays_and_discretize():
     with torch.no_grad():
         f = net.sdf.forward_fused(verts, H.RATIO, False, False)[0].view(-1)
     assert float(f.abs().max()) < 5e-3   # vertices sit on the zero set up to the linear edge interpolation (65^3 grid)
+
+
+def _one_step(net, data, rays, fids, fused, conf):
+    """forward_rays (eikonal + colour + normal + def_regu + offset) -> backward -> propagateTmpPsGrad with the
+    training evaluations on the tensor-core training engine (fused) or on torch autograd (cuBLAS)."""
+    from selfreconcode_b200 import train_ops
+    dev = "cuda"
+    N, Hh, Ww = fids.numel(), data.H, data.W
+    train_ops.TC_TRAIN_ENABLED = fused
+    net.conf = conf
+    g = torch.Generator().manual_seed(5)
+    img = (torch.rand(N, Hh, Ww, 3, generator=g) * 2 - 1).to(dev)
+    nrm = torch.nn.functional.normalize(torch.randn(N, Hh, Ww, 3, generator=g), dim=-1).to(dev)
+    params = [q for q in list(net.sdf.parameters()) + list(net.deformer.parameters()) +
+              list(net.netRender.parameters()) + list(data.parameters()) if q.requires_grad]
+    for q in params:
+        q.grad = None
+    torch.manual_seed(9)     # sample_points draws from the global generators
+    bi, ri, ci = rays["batch_inds"].to(dev), rays["rows"].to(dev), rays["cols"].to(dev)
+    loss = net.forward_rays({"img": img, "normal": nrm}, bi, ri, ci, rays["init_pts"].to(dev).clone(), H.RATIO, fids)
+    info = dict(net.info)
+    loss.backward()
+    gp = net.TmpPs.grad.detach().clone()
+    net.propagateTmpPsGrad(fids, H.RATIO)
+    grads = [q.grad.detach().clone() if q.grad is not None else None for q in params]
+    return loss.item(), info, gp, grads, params
+
+
+def test_training_step_fused_vs_autograd():
+    """The same optimisation step twice on the same GPU: training evaluations through the tensor-core training
+    engine (forward tangents + one reverse sweep, tcgen05 weight-gradient GEMMs) vs the torch-autograd twin
+    (create_graph=True double backward on cuBLAS): loss terms, dL/dTmpPs and every parameter gradient agree."""
+    from selfreconcode_b200 import synth, train_ops
+    net, data, rays, fids = build()
+    conf = synth.Conf(grad_weight=0.1, color_weight=0.5, normal_weight=0.1, weighted_normal=True, offset_weight=0.05,
+                      def_regu=dict(weight=2.0, c=0.5))
+    try:
+        la, ia, ga, gra, params = _one_step(net, data, rays, fids, False, conf)
+        lf, inf, gf, grf, _ = _one_step(net, data, rays, fids, True, conf)
+    finally:
+        train_ops.TC_TRAIN_ENABLED = True
+    print("loss autograd %.6f fused %.6f" % (la, lf), {k: (ia[k], inf[k]) for k in ia if k.endswith("_loss")})
+    assert abs(la - lf) < 2e-4 * max(1.0, abs(la))
+    for k in ("grad_loss", "color_loss", "normal_loss", "def_loss", "offset_loss"):
+        assert abs(ia[k] - inf[k]) < 2e-4 * max(1.0, abs(ia[k])), (k, ia[k], inf[k])
+    assert H.norm_err(gf.cpu().numpy(), ga.cpu().numpy()) < 2e-3
+    names = [n for n, q in list(net.sdf.named_parameters()) + list(net.deformer.named_parameters()) +
+             list(net.netRender.named_parameters()) + list(data.named_parameters()) if q.requires_grad]
+    worst = {}
+    for n, a, f in zip(names, gra, grf):
+        assert (a is None) == (f is None), n
+        if a is not None and float(a.abs().max()) > 0:
+            worst[n] = H.norm_err(f.cpu().numpy(), a.cpu().numpy())
+    top = sorted(worst.items(), key=lambda kv: -kv[1])[:6]
+    print("largest gradient differences:", top)
+    assert max(worst.values()) < 5e-3, top
