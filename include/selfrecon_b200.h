@@ -299,6 +299,13 @@ int sr_tc_linear(const void* A, const void* W, const float* bias, int64_t M, int
                  int out_col0, int out_n, float* dstash, const void* mul_tiles, int mul_K, int mul_act,
                  float mul_scale, const int32_t* m_dev, cudaStream_t s);
 
+/* Mesh rasteriser for the ray seed (replaces pytorch3d.renderer.MeshRasterizer in model/network.py:492 / :345 with
+ * faces_per_pixel = 1, blur_radius = 0, perspective_correct = True; consumer: utils/FindSurfacePs.py:5-29).
+ * verts_screen [N,V,3] = (pixel x = column, pixel y = row, camera depth z); faces [F,3] int64; keys = scratch of
+ * N*H*W uint64.  pix_to_face [N,H,W] int64 (n*F + f, -1 = empty), bary [N,H,W,3], zbuf [N,H,W] or NULL. */
+int sr_raster_mesh(const float* verts_screen, const int64_t* faces, int64_t N, int64_t V, int64_t F, int H, int W,
+                   uint64_t* keys, int64_t* pix_to_face, float* bary, float* zbuf, cudaStream_t s);
+
 /* Training half of the tensor-core engine (model/network.py:599-639, 774-796: loss.backward() and the parameter
  * VJPs of the implicit differentiation).  sr_tc_linear with mul_tiles != NULL is the reverse sweep of one layer; with
  * ch == 4 it propagates the cotangents of forward-mode rows (value + 3 tangents per point), i.e. second order.

@@ -134,22 +134,59 @@ def _install_stubs():
     fm.Fast3x3Minv_backward = Fast3x3Minv_backward
     sys.modules["FastMinv"] = fm
 
-    # ---- GridSamplerMine (first order only; enough for the forward oracle) ----
+    # ---- GridSamplerMine: forward / backward / dbackward from ONE differentiable torch restatement of the
+    #      sampler (trilinear, border padding, align_corners=False: MCAcc/cuda/GridSamplerMineKernel.cu:160-309),
+    #      so first and second order are consistent with each other on CPU ----
     gs = types.ModuleType("GridSamplerMine")
 
+    def _trilinear(inp, grid):
+        n, c, D, H, W = inp.shape
+        assert n == 1
+        g = grid.reshape(-1, 3)
+        size = torch.tensor([W, H, D], dtype=g.dtype)
+        ix = ((g + 1.0) * size - 1.0) / 2.0
+        ix = torch.minimum(torch.maximum(ix, torch.zeros(3, dtype=g.dtype)), size - 1.0)     # border clip
+        i0 = torch.floor(ix.detach())
+        fr = ix - i0
+        i0 = i0.long()
+        vol = inp[0].reshape(c, -1)
+        out = 0.0
+        for dz in (0, 1):
+            for dy in (0, 1):
+                for dx in (0, 1):
+                    xi = (i0[:, 0] + dx).clamp(max=W - 1)
+                    yi = (i0[:, 1] + dy).clamp(max=H - 1)
+                    zi = (i0[:, 2] + dz).clamp(max=D - 1)
+                    w = (fr[:, 0] if dx else 1 - fr[:, 0]) * (fr[:, 1] if dy else 1 - fr[:, 1]) * \
+                        (fr[:, 2] if dz else 1 - fr[:, 2])
+                    out = out + vol[:, (zi * H + yi) * W + xi] * w.unsqueeze(0)
+        return out.reshape((1, c) + tuple(grid.shape[1:4]))
+
     def gs_forward(inp, grid, interp=0, pad=1):
-        return F.grid_sample(inp, grid, mode="bilinear", padding_mode="border", align_corners=False)
+        with torch.no_grad():
+            return _trilinear(inp, grid)
 
     def gs_backward(inp, grid, gout, interp=0, pad=1):
         with torch.enable_grad():
             i = inp.detach().requires_grad_(True)
             g = grid.detach().requires_grad_(True)
-            o = F.grid_sample(i, g, mode="bilinear", padding_mode="border", align_corners=False)
-            gi, gg = torch.autograd.grad(o, [i, g], gout)
+            gi, gg = torch.autograd.grad(_trilinear(i, g), [i, g], gout)
         return gi, gg
+
+    def gs_dbackward(gg_inp, gg_grid, inp, grid, gout, interp=0, pad=1):
+        with torch.enable_grad():
+            i = inp.detach().requires_grad_(True)
+            g = grid.detach().requires_grad_(True)
+            go = gout.detach().requires_grad_(True)
+            gi, gg = torch.autograd.grad(_trilinear(i, g), [i, g], go, create_graph=True)
+            s = (gi * gg_inp).sum() + (gg * gg_grid).sum()
+            a, b, c = torch.autograd.grad(s, [i, g, go], allow_unused=True)
+        z = lambda t, like: torch.zeros_like(like) if t is None else t
+        return z(a, inp), z(b, grid), z(c, gout)
 
     gs.forward = gs_forward
     gs.backward = gs_backward
+    gs.dbackward = gs_dbackward
     sys.modules["GridSamplerMine"] = gs
 
 

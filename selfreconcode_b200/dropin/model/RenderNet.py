@@ -8,7 +8,7 @@ import torch.nn as nn
 
 from selfreconcode_b200 import ops
 from .Embedder import get_embedder
-from ._fused import (FoldCache, needs_autograd, ratio_value, require_cuda, SR_ACT_RELU,
+from ._fused import (FoldCache, needs_autograd, ratio_value, require_cuda, SR_ACT_NONE, SR_ACT_RELU,
                      SR_ACT_TANH)
 
 

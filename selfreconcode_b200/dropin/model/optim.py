@@ -90,6 +90,29 @@ class OptimNetwork(nn.Module):
         self.TmpPs = None
         self.raster_seed = None   # callable(frame_ids, TmpVs, Tmpfs, defconds, ratio) -> seed dict
 
+    # ---- differentiable value-only evaluations (tensor-core training engine when the modules are the stock ones)
+    def _sdf_value(self, pts, ratio):
+        if utils.train_fused(self.deformer, self.sdf):
+            return self.sdf.forward_train(pts, ratio, want_grad=False, want_feat=False)[0]
+        return self.sdf(pts, ratio)
+
+    def _deform(self, ps, conds, batch_inds, ratio):
+        if utils.train_fused(self.deformer):
+            return self.deformer.forward_train(ps, conds, batch_inds, ratio, want_jac=False)[0]
+        return self.deformer(ps, conds, batch_inds, ratio=ratio)
+
+    def _offset(self, ps, d_cond, ratio):
+        """translator offsets in mesh mode ps [N,M,3] (network.py:553, 571)."""
+        tr = self.deformer.defs[0]
+        if utils.train_fused(self.deformer):
+            n, m = ps.shape[0], ps.shape[1]
+            cr = d_cond.view(n, 1, -1).expand(n, m, d_cond.shape[-1]).reshape(n * m, -1)
+            off, _ = tr.forward_train(ps.reshape(-1, 3), cr, ratio, want_jac=False)
+            tr.offset = off.view(n, m, 3)
+            return tr.offset
+        tr(ps, d_cond, ratio=ratio)
+        return tr.offset
+
     # ---- cameras ----------------------------------------------------------------------------
     def _cameras(self, n, device):
         focals, pps, Rs, Ts, H, W = self.dataset.get_camera_parameters(n, device)
@@ -331,8 +354,8 @@ class OptimNetwork(nn.Module):
         if 'offset_weight' in conf and conf.get_float('offset_weight') >= 0.:
             w = conf.get_float('offset_weight')
             with torch.set_grad_enabled(w > 0.):
-                tr(eik_pts.view(1, -1, 3).expand(N, -1, 3), d_cond, ratio=ratio)
-                off = tr.offset.view(-1, 3).norm(p=2, dim=-1).mean()
+                off = self._offset(eik_pts.view(1, -1, 3).expand(N, -1, 3), d_cond, ratio)
+                off = off.reshape(-1, 3).norm(p=2, dim=-1).mean()
             self.info['offset_loss'] = off.item()
             if w > 0.:
                 out = out + off * w
@@ -376,6 +399,10 @@ class OptimNetwork(nn.Module):
             if isinstance(r, dict):
                 return r['batch_inds'], r['row_inds'], r['col_inds'], r['initTmpPs'], r.get('front_face_ids')
             return utils.FindSurfacePs(TmpVs.detach(), Tmpfs, r)
+        from .raster import SilhouetteRenderer
+        if isinstance(self.maskRender, SilhouetteRenderer):      # built-in device rasteriser (csrc/raster.cu)
+            _, frags = self.maskRender(defTmpVs.detach(), Tmpfs)
+            return utils.FindSurfacePs(TmpVs.detach(), Tmpfs, frags)
         P = _p3d()
         meshes = P.Meshes(verts=[v.view(V, 3) for v in torch.split(defTmpVs.detach(), 1)], faces=[Tmpfs] * N)
         _, frags = self.maskRender(meshes)
@@ -408,7 +435,7 @@ class OptimNetwork(nn.Module):
             self.root = root
         poses, trans, d_cond, _ = self.dataset.get_grad_parameters(frame_ids, device)
         defconds = [d_cond, [poses, trans]]
-        defTmpVs = self.deformer(self.TmpVs[None, :, :].expand(N, -1, 3), defconds, ratio=ratio)
+        defTmpVs = self._deform(self.TmpVs[None, :, :].expand(N, -1, 3), defconds, None, ratio)
         with torch.no_grad():
             bi, ri, ci, ps, _ = self._mesh_seed(defTmpVs, self.TmpVs, self.Tmpfs)
         pc_loss = self._pc_silhouette_loss(defTmpVs, defconds, gtMs, H, W, ratio)
@@ -441,12 +468,18 @@ class OptimNetwork(nn.Module):
                 return torch.zeros((), device=defTmpVs.device)
             raise RuntimeError("OptimNetwork.forward: no point renderer (pcRender) -- install pytorch3d, inject one, "
                                "or set allow_missing_pc_loss=True to train without the silhouette term")
-        P = _p3d()
         N, V = defTmpVs.shape[0], self.TmpVs.shape[0]
-        meshes = P.Meshes(verts=[v.view(V, 3) for v in torch.split(defTmpVs, 1)], faces=[self.Tmpfs] * N)
-        feats = [torch.ones(V, 1, device=defTmpVs.device) for _ in range(N)]
-        masks, _ = self.pcRender(P.Pointclouds(points=meshes.verts_list(), features=feats))
-        radius = self.pcRender.rasterizer.raster_settings.radius
+        if getattr(self.pcRender, "takes_tensors", False):
+            # a point renderer working on the [N,V,3] tensor directly (no pytorch3d containers)
+            masks = self.pcRender(defTmpVs)
+            radius = float(getattr(self.pcRender, "radius", 0.0))
+            meshes = defTmpVs
+        else:
+            P = _p3d()
+            meshes = P.Meshes(verts=[v.view(V, 3) for v in torch.split(defTmpVs, 1)], faces=[self.Tmpfs] * N)
+            feats = [torch.ones(V, 1, device=defTmpVs.device) for _ in range(N)]
+            masks, _ = self.pcRender(P.Pointclouds(points=meshes.verts_list(), features=feats))
+            radius = self.pcRender.rasterizer.raster_settings.radius
         radius = int(np.round(radius / 2. * float(min(H, W)) / 1.2))
         target = gtMs
         if radius > 0:
@@ -466,20 +499,23 @@ class OptimNetwork(nn.Module):
         self.info['pc_loss']['mask_loss'] = mask_loss.item()
         loss = mask_loss * (conf.get_float('pc_weight.mask_weight') if 'pc_weight.mask_weight' in conf else 1.)
         has_pc = 'pc_weight' in conf
-        P = _p3d()
-        tmpMesh = P.Meshes(verts=[self.TmpVs], faces=[self.Tmpfs])
-        for key, tag, fn in (('laplacian_weight', 'lap_loss', lambda m: P.mesh_laplacian_smoothing(m, method='uniform')),
-                             ('edge_weight', 'edge_loss', lambda m: P.mesh_edge_loss(m, target_length=0.)),
-                             ('norm_weight', 'norm_loss', P.mesh_normal_consistency)):
-            w = conf.get_float('pc_weight.' + key) if has_pc else -1.
+        tmpMesh = None
+        for key, tag, fn in (('laplacian_weight', 'lap_loss', lambda P, m: P.mesh_laplacian_smoothing(m, method='uniform')),
+                             ('edge_weight', 'edge_loss', lambda P, m: P.mesh_edge_loss(m, target_length=0.)),
+                             ('norm_weight', 'norm_loss', lambda P, m: P.mesh_normal_consistency(m))):
+            w = conf.get_float('pc_weight.' + key) if (has_pc and ('pc_weight.' + key) in conf) else -1.
             if w > 0.:
-                term = w * fn(tmpMesh)
+                P = _p3d()      # pytorch3d's mesh regularisers (third party, outside the hot path)
+                if tmpMesh is None:
+                    tmpMesh = P.Meshes(verts=[self.TmpVs], faces=[self.Tmpfs])
+                term = w * fn(P, tmpMesh)
                 loss = loss + term
                 self.info['pc_loss'][tag] = term.item() / w
         cw = conf.get_float('pc_weight.def_consistent.weight') if 'pc_weight.def_consistent' in conf else -1.
         if cw > 0.:
             rigid = self.deformer.defs[1](self.TmpVs.view(1, -1, 3).expand(N, -1, 3), defconds[1])
-            d2 = ((defMeshes.verts_padded() - rigid) ** 2).sum(-1)
+            dv = defMeshes if torch.is_tensor(defMeshes) else defMeshes.verts_padded()
+            d2 = ((dv - rigid) ** 2).sum(-1)
             c = conf.get_float('pc_weight.def_consistent.c')
             cl = utils.GMRobustError(d2, c, True).mean() if c > 0. else torch.sqrt(d2).mean()
             self.info['pc_loss']['defconst_loss'] = cl.item()
@@ -487,7 +523,7 @@ class OptimNetwork(nn.Module):
         self.TmpOptimizer.zero_grad()
         loss.backward()
         self.TmpOptimizer.step()
-        sdf_loss = (self.sdf(self.TmpVs, ratio).view(-1) + self.sdfShrinkRadius).abs().mean()
+        sdf_loss = (self._sdf_value(self.TmpVs, ratio).view(-1) + self.sdfShrinkRadius).abs().mean()
         self.info['pc_loss_sdf'] = sdf_loss.item()
         return sdf_loss * (conf.get_float('pc_weight.weight') if has_pc else 60.)
 
@@ -677,32 +713,13 @@ def getOptNet(dataset, N, bmins, bmaxs, resolutions, device, conf, use_initial_s
     return optNet, sdf_initialized
 
 
-class _CameraHolder:
-    """Minimal `maskRender` when pytorch3d is absent: carries `.rasterizer.cameras` (what the ray path reads)
-    and raises if asked to rasterise."""
-
-    class _Ras:
-        def __init__(self, cameras):
-            self.cameras = cameras
-
-        def to(self, device):
-            return self
-
-    def __init__(self, cameras):
-        self.rasterizer = _CameraHolder._Ras(cameras)
-
-    def to(self, device):
-        return self
-
-    def __call__(self, *a, **k):
-        raise RuntimeError("mesh silhouette rendering needs pytorch3d (or set OptimNetwork.raster_seed)")
-
-
 def _silhouette_renderer(cameras, H, W):
     try:
         P = _p3d()
     except RuntimeError:
-        return _CameraHolder(cameras)
+        # no pytorch3d: the built-in device rasteriser provides the fragments the ray seed needs
+        from .raster import MeshRasterizer, RasterSettings, SilhouetteRenderer
+        return SilhouetteRenderer(MeshRasterizer(cameras, RasterSettings((H, W))))
     settings = P.RasterizationSettings(image_size=(H, W), blur_radius=0.,
                                        bin_size=int(2 ** max(np.ceil(np.log2(max(H, W))) - 4, 4)),
                                        faces_per_pixel=1, perspective_correct=True, clip_barycentric_coords=False,

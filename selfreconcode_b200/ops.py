@@ -87,6 +87,28 @@ def minv3x3_backward(grads, invs):
     return outs
 
 
+def raster_mesh(verts_screen, faces, H, W):
+    """verts_screen [N,V,3] (pixel x, pixel y, depth), faces [F,3] int64 -> (pix_to_face [N,H,W,1] int64,
+    bary [N,H,W,1,3], zbuf [N,H,W,1]): pytorch3d Fragments layout with one face per pixel."""
+    _need_cuda(verts_screen, faces)
+    vs = verts_screen.detach().contiguous().float()
+    fc = faces.contiguous().to(torch.int64)
+    N, V, _ = vs.shape
+    F = fc.shape[0]
+    dev = vs.device
+    keys = torch.empty((N, H, W), dtype=torch.int64, device=dev)
+    p2f = torch.empty((N, H, W, 1), dtype=torch.int64, device=dev)
+    bary = torch.empty((N, H, W, 1, 3), dtype=torch.float32, device=dev)
+    zbuf = torch.empty((N, H, W, 1), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().sr_raster_mesh(_p(vs), _p(fc), N, V, F, int(H), int(W), _p(keys), _p(p2f), _p(bary),
+                                         _p(zbuf), _stream()), "raster_mesh")
+    return p2f, bary, zbuf
+
+
+_KERNELS_PER_CALL["raster_mesh"] = 2
+
+
 def svals3x3(J, want_v=True):
     """J [n,3,3] f32 CUDA -> (singular values [n,3] descending, V [n,3,3] | None)."""
     _need_cuda(J)

@@ -62,6 +62,7 @@ class _Workspace:
 
 
 COLSUM_SLICES = 64
+DEBUG_LAST = None      # tests: set to a dict to receive the tiles kept by the last forward (acts, shapes)
 
 
 class TcMlpFunction(torch.autograd.Function):
@@ -106,7 +107,8 @@ class TcMlpFunction(torch.autograd.Function):
         ctx.cfg, ctx.M, ctx.ld, ctx.L = cfg, M, ld, L
         ctx.A_in, ctx.acts, ctx.Ws = A_in, acts, Ws
         ctx.has_bias = [b is not None for b in bs]
-        ctx.x0_needs = None
+        if DEBUG_LAST is not None:
+            DEBUG_LAST.update(acts=acts, M=M, widths=[w.shape[0] for w in Ws], kpads=[_pad(w.shape[1], 32) for w in Ws])
         return out
 
     @staticmethod
@@ -176,6 +178,15 @@ class TcMlpFunction(torch.autograd.Function):
                 x0_grad[:, :cfg.d_in] += g_skip[:, :cfg.d_in]
         ctx.acts = ctx.A_in = None
         return (x0_grad, None) + tuple(grads)
+
+
+def unpack_tiles(tiles, M, K):
+    """tiled split-bf16 activations -> fp32 [M, K] (tests / debugging)."""
+    lib = _lib.load()
+    out = torch.empty((M, K), dtype=torch.float32, device=tiles.device)
+    with torch.cuda.device(tiles.device):
+        check(lib.sr_tc_unpack_rows(_p(tiles), M, K, _pad(K, 32), _p(out), K, _stream()), "tc_unpack_rows")
+    return out
 
 
 def tc_mlp(x0, cfg, weights, biases):
