@@ -447,7 +447,8 @@ def main():
     for _ in range(max(2, args.steps // 2)):
         flush.zero_()
         for m in (sc["sdf"], sc["comp"].defs[0], sc["rn"]):
-            m._cache.sig = None
+            with torch.no_grad():
+                next(iter(m.parameters())).add_(0.0)      # bumps Tensor._version like optimizer.step(): refold in place
         a, b = ev(), ev()
         a.record()
         ray_part(sc, rays_d, init_d, bi_d)

@@ -307,10 +307,13 @@ int sr_raster_mesh(const float* verts_screen, const int64_t* faces, int64_t N, i
                    uint64_t* keys, int64_t* pix_to_face, float* bary, float* zbuf, cudaStream_t s);
 
 /* Training half of the tensor-core engine (model/network.py:599-639, 774-796: loss.backward() and the parameter
- * VJPs of the implicit differentiation).  sr_tc_linear with mul_tiles != NULL is the reverse sweep of one layer; with
+ * VJPs; in a reverse launch (`mul_tiles` != NULL) `dstash` is an INPUT: the fp32 act'(z) the forward launch of the
+ * previous layer wrote (leading dimension = that layer's width rounded up to 256), or NULL to recompute act' from the
+ * activation tiles.
+ * sr_tc_linear with mul_tiles != NULL is the reverse sweep of one layer; with
  * ch == 4 it propagates the cotangents of forward-mode rows (value + 3 tangents per point), i.e. second order.
  *   sr_tc_wgrad   dW[N x K] (row-major, ld) = delta^T x over M rows; delta / x = tiled split-bf16 activations with
- *                 Kd / Kx feature columns (Kd padded to a multiple of 128 by the caller); `part` = scratch of
+ *                 Kd / Kx feature columns (each a multiple of 32); `part` = scratch of
  *                 sr_tc_wgrad_partial_bytes(M, Kd, Kx, NULL) bytes.  tcgen05 with MN-major operands: no transposes.
  *   sr_tc_colsum  partial[slice][k] = sum over rows with row % ch == 0 (value rows) of the tiled activations: the
  *                 bias gradient after a sum over slices.

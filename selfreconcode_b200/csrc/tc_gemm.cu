@@ -157,6 +157,9 @@ __device__ __forceinline__ void epi_chunk(const LayerArgs& a, const EpiRow& r, u
       const __nv_bfloat16* mt = a.mul_tiles + a_tile_off(r.mt, c0 >> 5, a.mul_KC, 0) +
                                 (size_t)(r.row_in_tile >> 3) * 64 + (r.row_in_tile & 7) * 8;
       const float kk = -144.26950408889634f * a.mul_inv_scale;   // -100 log2(e) / scale
+      // optional fp32 act'(z) of the previous layer's VALUE rows (written by its forward launch as `dstash`)
+      const float* stash = a.dstash == nullptr ? nullptr
+                           : a.dstash + (size_t)(CH == 4 ? (r.row & ~3LL) : r.row) * r.ds_ld + c0;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const uint4 q0 = *reinterpret_cast<const uint4*>(mt + (size_t)g * (BM * 8));
@@ -171,8 +174,11 @@ __device__ __forceinline__ void epi_chunk(const LayerArgs& a, const EpiRow& r, u
           float val = __uint_as_float(v[j]);
           if constexpr (CH == 1) {
             float d;
-            if constexpr (ACT == SR_ACT_SOFTPLUS100) d = 1.0f - fast_ex2(kk * as);
-            else if constexpr (ACT == SR_ACT_RELU) d = as > 0.f ? 1.f : 0.f;
+            if constexpr (ACT == SR_ACT_SOFTPLUS100) {
+              // training: act'(z) kept in fp32 by the forward sweep (recomputing it from the 16-bit-mantissa
+              // activation tiles costs 100 x 2^-17 relative on 1 - act'); the tracer recomputes (no stash traffic)
+              d = (stash != nullptr && r.row_ok && c0 + j < a.n) ? stash[j] : 1.0f - fast_ex2(kk * as);
+            } else if constexpr (ACT == SR_ACT_RELU) d = as > 0.f ? 1.f : 0.f;
             else d = 1.f;
             if (c0 + j < a.n) val = r.row_ok ? val * d : 0.f;
           } else {
@@ -184,8 +190,9 @@ __device__ __forceinline__ void epi_chunk(const LayerArgs& a, const EpiRow& r, u
             // and act'' u_c = 100 (1 - act') t_c for softplus(beta = 100), 0 for ReLU -- no division by act'.
             const float av = __shfl_sync(0xffffffffu, as, r.lane & ~3);   // the point's value-row activation
             float d;
-            if constexpr (ACT == SR_ACT_SOFTPLUS100) d = 1.0f - fast_ex2(kk * av);
-            else if constexpr (ACT == SR_ACT_RELU) d = av > 0.f ? 1.f : 0.f;
+            if constexpr (ACT == SR_ACT_SOFTPLUS100) {
+              d = (stash != nullptr && r.row_ok && c0 + j < a.n) ? stash[j] : 1.0f - fast_ex2(kk * av);
+            } else if constexpr (ACT == SR_ACT_RELU) d = av > 0.f ? 1.f : 0.f;
             else d = 1.f;
             float cross = 0.f;
             if constexpr (ACT == SR_ACT_SOFTPLUS100) {

@@ -39,7 +39,7 @@ constexpr int kWgThreads = 64 + 4 * 32;
 static_assert(kPlanes == 2, "the weight-gradient kernel is written for 2 planes / 3 terms");
 
 struct WgradArgs {
-  const __nv_bfloat16* D;   // delta tiles [MT][KCd][planes][128x32], KCd % 4 == 0
+  const __nv_bfloat16* D;   // delta tiles [MT][KCd][planes][128x32]
   const __nv_bfloat16* X;   // input tiles [MT][KCx][planes][128x32]
   int MT, KCd, KCx;
   int tiles_n;              // ceil(KCx / 8)
@@ -77,6 +77,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
   const int tile = blockIdx.x / a.splits, split = blockIdx.x % a.splits;
   const int tm = tile / a.tiles_n, tn = tile % a.tiles_n;
   const int nb = min(8, a.KCx - tn * 8);              // 32-feature chunks of x in this tile (MMA N = 32 nb)
+  const int na = min(4, a.KCd - tm * 4);              // 32-feature chunks of delta in this tile; a short last tile
+                                                      // leaves stale shared memory in the other rows of the M = 128
+                                                      // operand: those accumulator rows are simply never stored
   const int halves = 2 * a.MT;
   const int per = (halves + a.splits - 1) / a.splits;
   const int h0 = split * per, h1 = min(halves, h0 + per);
@@ -92,15 +95,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
       const int half = h & 1;
       if (lane == 0) {
         sr_mbar_wait(&empty[slot], phase ^ 1u);
-        sr_mbar_arrive_expect_tx(&full[slot], (uint32_t)(32 + nb * 8) * 1024u);
+        sr_mbar_arrive_expect_tx(&full[slot], (uint32_t)(na * 8 + nb * 8) * 1024u);
       }
       __syncwarp();
       unsigned char* st = smem + (size_t)slot * WG_STAGE_BYTES;
       {  // delta: plane p, feature group g (8 features) of this tile's 128
         const int p = lane >> 4, g = lane & 15;
-        const __nv_bfloat16* src = a.D + a_tile_off(mt, tm * 4 + (g >> 2), a.KCd, p) + (size_t)(g & 3) * (BM * 8) +
-                                   (size_t)half * (WG_ROWS * 8);
-        sr_bulk_g2s(st + p * WG_A_PLANE_BYTES + g * 1024, src, 1024u, &full[slot]);
+        if ((g >> 2) < na) {
+          const __nv_bfloat16* src = a.D + a_tile_off(mt, tm * 4 + (g >> 2), a.KCd, p) + (size_t)(g & 3) * (BM * 8) +
+                                     (size_t)half * (WG_ROWS * 8);
+          sr_bulk_g2s(st + p * WG_A_PLANE_BYTES + g * 1024, src, 1024u, &full[slot]);
+        }
       }
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
@@ -156,6 +161,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
     // ------------------------------------------------------------------ drain (warps 2..5)
     const int q = warp & 3;                               // TMEM lane quarter of this warp
     const int row = tm * 128 + q * 32 + lane;             // delta feature
+    const bool row_ok = row < a.KCd * 32;
     const size_t ld = (size_t)a.KCx * 32;
     float* dst = a.part + ((size_t)split * ((size_t)a.KCd * 32) + row) * ld + (size_t)tn * 256;
     for (int run = 0; run < nruns; ++run) {
@@ -167,6 +173,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
         uint32_t v[32];
         tmem_ld32_async(taddr0 + c * 32, v);
         tmem_wait(v);
+        if (!row_ok) continue;
         float4* d4 = reinterpret_cast<float4*>(dst + c * 32);
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
@@ -183,7 +190,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
       __syncwarp();
       if (lane == 0) sr_mbar_arrive(&tempty[buf]);
     }
-    if (nruns == 0) {   // a split without rows still owns its partial tile
+    if (nruns == 0 && row_ok) {   // a split without rows still owns its partial tile
       for (int c = 0; c < nb * 8; ++c) reinterpret_cast<float4*>(dst)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
@@ -280,7 +287,7 @@ int sr_tc_wgrad(const void* D, int Kd, const void* X, int Kx, int64_t M, float* 
   WgradArgs a;
   a.D = (const __nv_bfloat16*)D; a.X = (const __nv_bfloat16*)X;
   a.MT = (int)((M + BM - 1) / BM); a.KCd = (Kd + 31) / 32; a.KCx = (Kx + 31) / 32;
-  if (a.KCd % 4 != 0 || N > a.KCd * 32 || K > a.KCx * 32) return SR_EINVAL;
+  if (N > a.KCd * 32 || K > a.KCx * 32) return SR_EINVAL;
   a.tiles_n = (a.KCx + 7) / 8;
   int splits = 1;
   sr_tc_wgrad_partial_bytes(M, Kd, Kx, &splits);
@@ -294,7 +301,7 @@ int sr_tc_wgrad(const void* D, int Kd, const void* X, int Kx, int64_t M, float* 
     if (e != cudaSuccess) return (int)e;
     attr_set_dev[cur_dev & 63] = true;
   }
-  const int tiles = (a.KCd / 4) * a.tiles_n;
+  const int tiles = ((a.KCd + 3) / 4) * a.tiles_n;
   tc_wgrad_kernel<<<tiles * splits, kWgThreads, kSmemWgrad, s>>>(a);
   int rc = sr_launch_status();
   if (rc) return rc;

@@ -164,7 +164,8 @@ class MLPTranslator(nn.Module):
         d_in = 3 + 6 * self.multires + self.feature_vector_size
         pe_w = ops.annealing_weights(self.multires, ratio_value(ratio, "deformerRatio"))
         x0 = T.embed_rows(pts, self.multires, pe_w, ch, extra=cond_rows)
-        out = T.tc_mlp(x0, T.MlpConfig(acts, [False] * L, d_in, ch), Ws, bs).view(pts.shape[0], ch, 3)
+        packs = ops.tc_net(self.fused(ratio)).layers
+        out = T.tc_mlp(x0, T.MlpConfig(acts, [False] * L, d_in, ch, packs), Ws, bs).view(pts.shape[0], ch, 3)
         off = out[:, 0]
         jac = out[:, 1:].transpose(1, 2) if want_jac else None      # [P, m, c] = d off_m / d p_c
         return off, jac

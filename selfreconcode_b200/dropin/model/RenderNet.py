@@ -79,7 +79,8 @@ class RenderingNetwork_view_norm(nn.Module):
         x = torch.cat([points, ev, normals, feature_vectors], dim=-1)
         x0 = torch.nn.functional.pad(x, (0, (-x.shape[1]) % 32))
         acts = [SR_ACT_RELU] * (L - 1) + [SR_ACT_NONE]
-        out = T.tc_mlp(x0, T.MlpConfig(acts, [False] * L, x.shape[1], 1), Ws, bs)
+        packs = ops.tc_net(self.fused(ratio)).layers
+        out = T.tc_mlp(x0, T.MlpConfig(acts, [False] * L, x.shape[1], 1, packs), Ws, bs)
         return torch.tanh(out)
 
     def forward(self, points, normals, view_dirs, feature_vectors, ratio):

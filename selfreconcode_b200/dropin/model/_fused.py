@@ -32,7 +32,14 @@ class FoldCache:
     def get(self, params, builder):
         sig = tuple((p.data_ptr(), p._version, str(p.device)) for p in params)
         if sig != self.sig:
-            self.net = builder()
-            self.extra = {}
+            same_storage = self.sig is not None and self.net is not None and \
+                tuple((a[0], a[2]) for a in sig) == tuple((a[0], a[2]) for a in self.sig)
+            if same_storage and hasattr(self.net, "refold"):
+                # only the VALUES changed (optimizer.step(), load_state_dict): refold into the same device buffers
+                # -- descriptors, tensor-core packs, truncated views and captured graphs stay valid
+                self.net.refold()
+            else:
+                self.net = builder()
+                self.extra = {}
             self.sig = sig
         return self.net

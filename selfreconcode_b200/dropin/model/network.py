@@ -148,7 +148,8 @@ class ImplicitNetwork(nn.Module):
             skips.append(l in self.skip_in)
         d_in = 3 + 6 * self.multires
         x0 = T.embed_rows(pts, self.multires, self._pe_weights(ratio_value(ratio, "sdfRatio")), ch)
-        out = T.tc_mlp(x0, T.MlpConfig(acts, skips, d_in, ch), Ws, bs).view(P, ch, -1)
+        packs = ops.tc_net(self.fused() if want_feat else self.fused_sdf_only()).layers
+        out = T.tc_mlp(x0, T.MlpConfig(acts, skips, d_in, ch, packs), Ws, bs).view(P, ch, -1)
         sdf = out[:, 0, :self.d_out]
         grad = out[:, 1:, 0] if want_grad else None
         feat = out[:, 0, self.d_out:] if (want_feat and out.shape[2] > self.d_out) else None

@@ -20,7 +20,9 @@ import os as _os
 # Tensor-core engine switch: large batches go to the tcgen05 split-BF16 layer GEMMs, small ones to the
 # fused fp32 FFMA engine (one persistent kernel, lower latency).  SELFRECON_B200_TC=0 disables it.
 TC_ENABLED = _os.environ.get("SELFRECON_B200_TC", "1") != "0"
-TC_MIN_POINTS = int(_os.environ.get("SELFRECON_B200_TC_MIN_POINTS", "16384"))
+# 2048: at the reference's real per-step batch (~6 144 rays, config.conf:3,113) a tensor-core trace is launch bound
+# (~4 ms, or one graph replay) while the fp32 engine needs ~20 ms
+TC_MIN_POINTS = int(_os.environ.get("SELFRECON_B200_TC_MIN_POINTS", "2048"))
 
 # Borderline decisions on tensor-core values are re-taken on the fp32 FFMA engine:
 # TC_EPS_F bounds the engine's absolute error on an SDF value (measured 2.4e-5 against fp64, csrc/tc_gemm.cu),
@@ -307,7 +309,9 @@ class FusedMLP:
         self.uid = next(_uid_counter)   # identity for caches (id() can be recycled)
 
     def fold(self, linears, pe_w=None):
-        lib = _lib.load()
+        """Folds (weight norm applied, transposed, padded) the given layers into this object's device buffers.
+        The buffers are allocated on the first call and REUSED afterwards (`refold`): descriptors, tensor-core
+        packs and captured CUDA graphs that point at them stay valid when the parameters change."""
         d = self.desc
         d.n_layers = len(linears)
         d.d_in = self.d_in
@@ -317,34 +321,48 @@ class FusedMLP:
             d.pe_w[i] = float(pw[i]) if i < len(pw) else 0.0
         if len(linears) > _lib.SR_MLP_MAX_LAYERS:
             raise RuntimeError("FusedMLP: too many layers")
-        bufs = []
+        self._linears = linears
+        self._lay = []
         with torch.cuda.device(self.device):
             for i, L in enumerate(linears):
-                v = L["v"].detach()
-                _need_cuda(v)
-                v = v.contiguous().float()
-                n, k = v.shape
+                n, k = L["v"].shape
+                _need_cuda(L["v"])
                 npad, kpad = _pad(n, 128), _pad(k, 8)
                 if npad > 512 or kpad > 512:
                     raise RuntimeError("FusedMLP: layer %dx%d exceeds the 512-wide engine" % (n, k))
                 wt = torch.empty((kpad, npad), dtype=torch.float32, device=self.device)
                 bias = torch.empty((npad,), dtype=torch.float32, device=self.device)
                 wb = torch.empty((_pad(n, 8), _pad(k, 128)), dtype=torch.float32, device=self.device)
-                g = L.get("g")
-                b = L.get("b")
-                g = g.detach().contiguous().float().view(-1) if g is not None else None
-                b = b.detach().contiguous().float() if b is not None else None
-                check(lib.sr_fold_linear(_p(v), _p(g), _p(b), n, k, npad, kpad, _p(wt), _p(bias),
-                                         _p(wb), _stream()), "fold_linear")
-                bufs += [wt, bias, v, g, b, wb]
+                self._lay.append(dict(wt=wt, bias=bias, wb=wb, n=n, k=k, npad=npad, kpad=kpad))
                 ly = d.layer[i]
-                ly.wt = wt.data_ptr()
-                ly.bias = bias.data_ptr()
-                ly.wb = wb.data_ptr()
+                ly.wt, ly.bias, ly.wb = wt.data_ptr(), bias.data_ptr(), wb.data_ptr()
                 ly.k, ly.n, ly.kpad, ly.npad = k, n, kpad, npad
                 ly.act = int(L["act"])
                 ly.skip = 1 if L.get("skip") else 0
-        self.bufs = bufs  # keep device buffers alive
+        self.bufs = [t for e in self._lay for t in (e["wt"], e["bias"], e["wb"])]
+        self._children = []
+        self.version = 0
+        self.refold()
+        return self
+
+    def refold(self):
+        """Re-runs the fold kernels from the current parameter values into the existing buffers, then refreshes
+        everything derived from them (truncated views, tensor-core packs)."""
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            for e, L in zip(self._lay, self._linears):
+                v = L["v"].detach().contiguous().float()
+                g, b = L.get("g"), L.get("b")
+                g = g.detach().contiguous().float().view(-1) if g is not None else None
+                b = b.detach().contiguous().float() if b is not None else None
+                check(lib.sr_fold_linear(_p(v), _p(g), _p(b), e["n"], e["k"], e["npad"], e["kpad"], _p(e["wt"]),
+                                         _p(e["bias"]), _p(e["wb"]), _stream()), "fold_linear")
+        self.version += 1
+        for c in self._children:
+            c._refresh_from_parent()
+        tc = getattr(self, "_tc", None)
+        if tc is not None:
+            tc.repack()
         return self
 
     def set_pe_weights(self, pe_w):
@@ -357,22 +375,34 @@ class FusedMLP:
         t = FusedMLP(self.d_in, self.multires, self.device)
         C.memmove(C.byref(t.desc), C.byref(self.desc), C.sizeof(MlpDesc))
         last = t.desc.layer[t.desc.n_layers - 1]
-        full_npad = last.npad
+        e = self._lay[-1]
         npad = _pad(n_out, 128)
-        if npad != full_npad:
+        t._own = None
+        if npad != e["npad"]:
             # W_T rows are npad-strided, so a narrower view needs its own copy of the columns
-            k, kpad = last.k, last.kpad
-            src = [b for b in self.bufs if b is not None and b.data_ptr() == last.wt][0]
-            bsrc = [b for b in self.bufs if b is not None and b.data_ptr() == last.bias][0]
-            wt = src[:, :npad].contiguous()
-            bias = bsrc[:npad].contiguous()
-            t.bufs = [wt, bias]
-            last.wt = wt.data_ptr()
-            last.bias = bias.data_ptr()
+            t._own = (e["wt"][:, :npad].contiguous(), e["bias"][:npad].contiguous(), npad)
+            last.wt = t._own[0].data_ptr()
+            last.bias = t._own[1].data_ptr()
             last.npad = npad
         last.n = n_out
         t._parent = self
+        t._lay = self._lay[:-1] + [dict(e, n=n_out, npad=npad, wt=t._own[0] if t._own else e["wt"],
+                                        bias=t._own[1] if t._own else e["bias"])]
+        t.bufs = [x for x in (t._own[:2] if t._own else [])]
+        t._children = []
+        t.version = self.version
+        self._children.append(t)
         return t
+
+    def _refresh_from_parent(self):
+        if self._own is not None:
+            e = self._parent._lay[-1]
+            self._own[0].copy_(e["wt"][:, :self._own[2]])
+            self._own[1].copy_(e["bias"][:self._own[2]])
+        self.version = self._parent.version
+        tc = getattr(self, "_tc", None)
+        if tc is not None:
+            tc.repack()
 
 
 def annealing_weights(multires, ratio):
@@ -724,8 +754,9 @@ def tc_linear(A, W, bias, M, N, K, n_valid, act, ch=1, K_next=0, scale=1.0, skip
 
 
 class TcNet:
-    """Tensor-core view of a FusedMLP: the same folded weights packed as tiled split-bf16 operands.
-    Built lazily from the FusedMLP's un-transposed padded copies (`wb`), cached on the FusedMLP."""
+    """Tensor-core view of a FusedMLP: the same folded weights packed as tiled split-bf16 operands -- `W` for the
+    forward sweep, `Wb` (= W^T) for the reverse sweep.  The pack buffers are persistent: `repack()` rewrites them
+    in place when the FusedMLP is refolded, so launches recorded in a CUDA graph keep reading current weights."""
 
     def __init__(self, fused):
         self.fused = fused
@@ -733,28 +764,28 @@ class TcNet:
         self.layers = []
         lib = _lib.load()
         dev = fused.device
-        wbs = [b for b in fused.bufs]
-        parent = getattr(fused, "_parent", None)  # truncated views share the parent's buffers
-        if parent is not None:
-            wbs += [b for b in parent.bufs]
         for i in range(d.n_layers):
             ly = d.layer[i]
+            e = fused._lay[i]
             n, k = ly.n, ly.k
-            wb = [b for b in wbs if b is not None and b.data_ptr() == ly.wb][0]
-            bias = [b for b in wbs if b is not None and b.data_ptr() == ly.bias][0]
             W = torch.empty((lib.sr_tc_weight_bytes(n, k),), dtype=torch.uint8, device=dev)
-            with torch.cuda.device(dev):
-                check(lib.sr_tc_pack_weights(_p(wb), n, k, wb.shape[1], _p(W), _stream()), "tc_pack_weights")
-            npad = _pad(n, 256)
-            b = torch.zeros((npad,), dtype=torch.float32, device=dev)
-            b[:n] = bias[:n]
-            # reverse sweep operand: W_l^T as [k rows][n cols] = the FFMA engine's W_T copy (ld = npad)
-            wt = [t for t in wbs if t is not None and t.data_ptr() == ly.wt][0]
             Wb = torch.empty((lib.sr_tc_weight_bytes(k, n),), dtype=torch.uint8, device=dev)
-            with torch.cuda.device(dev):
-                check(lib.sr_tc_pack_weights(_p(wt), k, n, wt.shape[1], _p(Wb), _stream()), "tc_pack_weights")
-            self.layers.append(dict(W=W, Wb=Wb, bias=b, n=n, k=k, act=ly.act, skip=bool(ly.skip),
+            self.layers.append(dict(W=W, Wb=Wb, bias=torch.zeros((_pad(n, 256),), dtype=torch.float32, device=dev),
+                                    n=n, k=k, act=ly.act, skip=bool(ly.skip), _e=e,
                                     zero_bias=torch.zeros((_pad(k, 256),), dtype=torch.float32, device=dev)))
+        self.repack()
+
+    def repack(self):
+        lib = _lib.load()
+        with torch.cuda.device(self.fused.device):
+            for L in self.layers:
+                e, n, k = L["_e"], L["n"], L["k"]
+                check(lib.sr_tc_pack_weights(_p(e["wb"]), n, k, e["wb"].shape[1], _p(L["W"]), _stream()),
+                      "tc_pack_weights")
+                # reverse sweep operand: W^T as [k rows][n cols] = the FFMA engine's W_T copy (ld = npad)
+                check(lib.sr_tc_pack_weights(_p(e["wt"]), k, n, e["wt"].shape[1], _p(L["Wb"]), _stream()),
+                      "tc_pack_weights")
+                L["bias"][:n].copy_(e["bias"][:n])
 
 
 def tc_net(fused):

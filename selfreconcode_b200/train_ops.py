@@ -32,11 +32,14 @@ INV_SQRT2 = 0.7071067811865476
 class MlpConfig:
     """Static description of one MLP stack for TcMlpFunction."""
 
-    def __init__(self, acts, skips, d_in, ch):
+    def __init__(self, acts, skips, d_in, ch, packs=None):
         self.acts = [int(a) for a in acts]
         self.skips = [bool(s) for s in skips]
         self.d_in = int(d_in)          # width of the embedded input that a skip layer re-appends
         self.ch = int(ch)
+        # optional: the module's persistent tensor-core packs (ops.TcNet.layers: W, Wb = W^T, padded bias) of the
+        # SAME weights that are passed as tensors -- then nothing is packed per call
+        self.packs = packs
 
 
 def _pack_weights(lib, w):
@@ -81,31 +84,41 @@ class TcMlpFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             A_in = torch.empty((lib.sr_tc_act_bytes(M, ld),), dtype=torch.uint8, device=dev)
             check(lib.sr_tc_pack_rows(_p(x0), M, ld, ld, _p(A_in), None, _stream()), "tc_pack_rows")
-            packed, acts = [], []
+            packed, acts, stashes = [], [], []
             cur, K = A_in, ld
             out = None
             for i in range(L):
                 n, k = Ws[i].shape
                 last = i == L - 1
-                Wp = _pack_weights(lib, Ws[i])
-                packed.append(Wp)
-                bias = torch.zeros((_pad(n, 256),), dtype=torch.float32, device=dev)
-                if bs[i] is not None:
-                    bias[:n] = bs[i].detach().float()
+                pk = cfg.packs[i] if cfg.packs is not None else None
+                if pk is not None and (pk["n"], pk["k"]) == (n, k):
+                    Wp, bias = pk["W"], pk["bias"]
+                else:
+                    pk = None
+                    Wp = _pack_weights(lib, Ws[i])
+                    bias = torch.zeros((_pad(n, 256),), dtype=torch.float32, device=dev)
+                    if bs[i] is not None:
+                        bias[:n] = bs[i].detach().float()
+                packed.append(pk)
                 skip_next = (not last) and cfg.skips[i + 1]
                 Kn = 0 if last else _pad(Ws[i + 1].shape[1], 32)
                 A_next = None if last else torch.empty((lib.sr_tc_act_bytes(M, Kn),), dtype=torch.uint8, device=dev)
                 if last:
                     out = torch.empty((M, n), dtype=torch.float32, device=dev)
+                # softplus(beta=100): keep act'(z) in fp32 for the reverse sweep (1 - act' recomputed from the
+                # 16-bit-mantissa activation tiles would carry 100 x 2^-17 of relative error into every gradient)
+                ds = torch.empty((M, _pad(n, 256)), dtype=torch.float32, device=dev) \
+                    if (not last and cfg.acts[i] == _lib.SR_ACT_SOFTPLUS100) else None
                 check(lib.sr_tc_linear(_p(cur), _p(Wp), _p(bias), M, n, K, n, cfg.acts[i], ch, _p(A_next), Kn,
                                        INV_SQRT2 if skip_next else 1.0, _p(x0) if skip_next else None,
-                                       cfg.d_in if skip_next else 0, ld, _p(out), n if last else 0, 0, n, None, None,
+                                       cfg.d_in if skip_next else 0, ld, _p(out), n if last else 0, 0, n, _p(ds), None,
                                        0, 0, 1.0, None, _stream()), "tc_linear")
                 if not last:
                     acts.append(A_next)
+                    stashes.append(ds)
                     cur, K = A_next, Kn
         ctx.cfg, ctx.M, ctx.ld, ctx.L = cfg, M, ld, L
-        ctx.A_in, ctx.acts, ctx.Ws = A_in, acts, Ws
+        ctx.A_in, ctx.acts, ctx.Ws, ctx.packed, ctx.stashes = A_in, acts, Ws, packed, stashes
         ctx.has_bias = [b is not None for b in bs]
         if DEBUG_LAST is not None:
             DEBUG_LAST.update(acts=acts, M=M, widths=[w.shape[0] for w in Ws], kpads=[_pad(w.shape[1], 32) for w in Ws])
@@ -122,14 +135,10 @@ class TcMlpFunction(torch.autograd.Function):
         grads = [None] * (2 * L)
         with torch.cuda.device(dev):
             n_last = Ws[-1].shape[0]
-            Kd = _pad(n_last, 128)
+            Kd = _pad(n_last, 32)
             g = gout.detach().contiguous().float()
-            if Kd != n_last:      # the tile buffer is Kd wide (a multiple of 128 for the wgrad M tiles): zero padded
-                gp = torch.zeros((M, Kd), dtype=torch.float32, device=dev)
-                gp[:, :n_last] = g
-                g = gp
             D = torch.empty((lib.sr_tc_act_bytes(M, Kd),), dtype=torch.uint8, device=dev)
-            check(lib.sr_tc_pack_rows(_p(g), M, Kd, Kd, _p(D), None, _stream()), "tc_pack_rows")
+            check(lib.sr_tc_pack_rows(_p(g), M, n_last, n_last, _p(D), None, _stream()), "tc_pack_rows")
             x0_grad = None
             g_skip = None
             for l in range(L - 1, -1, -1):
@@ -150,21 +159,24 @@ class TcMlpFunction(torch.autograd.Function):
                 if l == 0 and not need_x0:
                     break
                 # ---- reverse GEMM: cotangent of this layer's input
-                wt = torch.zeros((k, Kd), dtype=torch.float32, device=dev)
-                wt[:, :n] = Ws[l].t()
-                Wt = _pack_weights(lib, wt)
-                zb = torch.zeros((_pad(k, 256),), dtype=torch.float32, device=dev)
+                pk = ctx.packed[l]
+                if pk is not None:
+                    Wt, zb = pk["Wb"], pk["zero_bias"]
+                else:
+                    Wt = _pack_weights(lib, Ws[l].t().contiguous())          # [k rows, n cols]
+                    zb = torch.zeros((_pad(k, 256),), dtype=torch.float32, device=dev)
                 scale = INV_SQRT2 if cfg.skips[l] else 1.0
                 if l > 0:
                     n_prev = Ws[l - 1].shape[0]
-                    Kd_prev = _pad(n_prev, 128)
+                    Kd_prev = _pad(n_prev, 32)
                     D_prev = torch.empty((lib.sr_tc_act_bytes(M, Kd_prev),), dtype=torch.uint8, device=dev)
                     if cfg.skips[l]:
                         g_skip = torch.empty((M, _pad(cfg.d_in, 4)), dtype=torch.float32, device=dev)
                     check(lib.sr_tc_linear(_p(D), _p(Wt), _p(zb), M, k, Kd, n_prev, SR_ACT_NONE, ch, _p(D_prev), Kd_prev,
                                            scale, None, 0, 0, _p(g_skip) if cfg.skips[l] else None,
                                            g_skip.shape[1] if cfg.skips[l] else 0, n_prev,
-                                           cfg.d_in if cfg.skips[l] else 0, None, _p(ctx.acts[l - 1]), _pad(k, 32),
+                                           cfg.d_in if cfg.skips[l] else 0, _p(ctx.stashes[l - 1]), _p(ctx.acts[l - 1]),
+                                           _pad(k, 32),
                                            cfg.acts[l - 1], scale, None, _stream()), "tc_linear")
                     D, Kd = D_prev, Kd_prev
                 else:
@@ -176,7 +188,7 @@ class TcMlpFunction(torch.autograd.Function):
                         x0_grad[:, k:] = 0.0
             if x0_grad is not None and g_skip is not None:
                 x0_grad[:, :cfg.d_in] += g_skip[:, :cfg.d_in]
-        ctx.acts = ctx.A_in = None
+        ctx.acts = ctx.A_in = ctx.stashes = None
         return (x0_grad, None) + tuple(grads)
 
 

@@ -154,8 +154,11 @@ def test_optimisation_step_vs_reference_golden(cuda_dev):
     terms["mask_loss"] = (info["pc_loss"]["mask_loss"], float(g["info_mask_loss"]))
     terms["total"] = (loss.item(), float(g["loss"]))
     print({k: "%.6f / %.6f" % v for k, v in terms.items()})
+    # pc_loss_sdf = mean |f| over the template vertices (~1e-3): the tensor-core engine's ~1e-6 absolute error on f
+    # shows there, and 60x (the term's weight) in the total
+    atol = {"pc_loss_sdf": 5e-6, "total": 60 * 5e-6}
     for k, (a, b) in terms.items():
-        assert abs(a - b) < tol * 3e-4 * max(abs(b), 1e-3), (k, a, b)
+        assert abs(a - b) < tol * 3e-4 * max(abs(b), 1e-3) + atol.get(k, 0.0), (k, a, b)
     np.testing.assert_allclose(net.TmpVs.detach().cpu().numpy(), g["TmpVs_after"], atol=2e-6)
     if same_set:
         order = np.lexsort((net.col_inds.cpu().numpy(), net.row_inds.cpu().numpy(), net.batch_inds.cpu().numpy()))

@@ -32,7 +32,8 @@ def main():
     tr, sk = comp.defs
     for rep in range(2):
         for m in (sdf, tr, rn):
-            m._cache.sig = None
+            with torch.no_grad():
+                next(iter(m.parameters())).add_(0.0)      # bumps Tensor._version like optimizer.step(): refold in place
         ms_fold, nets = t(lambda: (sdf.fused_sdf_only(), sdf.fused(), tr.fused(bench.RATIO), rn.fused(bench.RATIO)))
         ms_pack, _ = t(lambda: [ops.tc_net(n) for n in nets])
         lbs = sk.lbs_state()
@@ -50,7 +51,8 @@ def main():
     os.environ["X"] = "1"
     ops.GRAPHS_ENABLED = False
     for m in (sdf, tr, rn):
-        m._cache.sig = None
+        with torch.no_grad():
+            next(iter(m.parameters())).add_(0.0)
     nets = (sdf.fused_sdf_only(), sdf.fused(), tr.fused(bench.RATIO), rn.fused(bench.RATIO))
     nets[0].set_pe_weights([1.0] * 6)
     lbs = sk.lbs_state()
