@@ -201,6 +201,138 @@ def ray_part_api(sc, rays, init, bi):
 
 
 # --------------------------------------------------------------------------------------------------
+# Training step (BASELINE configs[2] / [3]): batch of 4 frames per GPU, SMPL LBS + FastMinv on, eikonal + colour +
+# normal + def_regu + offset losses (config.conf loss_coarse), implicit differentiation, ONE NCCL all-reduce of all
+# gradients, Adam step -- train.py:160-171 with the per-point work on the tensor-core training engine.
+TRAIN_FRAMES = 4
+TRAIN_RAYS = 2048 * TRAIN_FRAMES      # config.conf sample_pix_num per frame
+
+
+def build_train(sc, dev, rank, world):
+    from selfreconcode_b200 import synth, parallel
+    from model.optim import OptimNetwork
+    from model.CameraMine import RectifiedPerspectiveCameras
+    import types
+    H = W = 512
+    data = synth.SyntheticDataset(TRAIN_FRAMES, H, W, seed=50 + rank).to(dev)
+    fids = torch.arange(TRAIN_FRAMES, device=dev)
+    poses, trans, dcond, _ = data.get_grad_parameters(fids, dev)
+    sdf, comp, rn = sc["sdf"], sc["comp"], sc["rn"]
+    with torch.no_grad():
+        rays = synth.make_rays(sc["cam"], TRAIN_FRAMES,
+                               lambda p: sdf.forward_fused(p.to(dev), RATIO, False, False)[0].view(-1),
+                               lambda p, b: comp.forward_fused(p.to(dev), [dcond, [poses, trans]], b.to(dev), RATIO)[0],
+                               seed=31 + rank, jitter=3e-4)
+    g = torch.Generator().manual_seed(77 + rank)
+    sel = torch.randperm(rays["rays"].shape[0], generator=g)[:TRAIN_RAYS].sort()[0]
+    f, pp, R, T, _, _ = data.get_camera_parameters(TRAIN_FRAMES, dev)
+    cams = RectifiedPerspectiveCameras(f.detach(), pp.detach(), R, T.detach(), image_size=[(W, H)])
+    holder = types.SimpleNamespace(rasterizer=types.SimpleNamespace(cameras=cams))
+    conf = synth.reference_config().get_config("loss_coarse")
+    net = OptimNetwork(sdf, comp, None, holder, rn, conf=conf)
+    net.dataset = data
+    params = [q for q in list(sdf.parameters()) + list(comp.parameters()) + list(rn.parameters()) +
+              list(data.parameters()) if q.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-5)
+    ar = parallel.GradAllReduce(params, timed=True)
+    img = (torch.rand(TRAIN_FRAMES, H, W, 3, generator=g) * 2 - 1).to(dev)
+    nrm = torch.nn.functional.normalize(torch.randn(TRAIN_FRAMES, H, W, 3, generator=g), dim=-1).to(dev)
+    extra = rays["pstar"][torch.randperm(rays["pstar"].shape[0], generator=g)[:4096]].to(dev)
+    return dict(net=net, opt=opt, ar=ar, fids=fids, datas={"img": img, "normal": nrm}, extra=extra, params=params,
+                bi=rays["batch_inds"][sel].to(dev), ri=rays["rows"][sel].to(dev), ci=rays["cols"][sel].to(dev),
+                init=rays["init_pts"][sel].to(dev))
+
+
+def train_step(tr, events=None):
+    net, opt = tr["net"], tr["opt"]
+    mark = (lambda i: events[i].record()) if events is not None else (lambda i: None)
+    mark(0)
+    opt.zero_grad(set_to_none=True)
+    loss = net.forward_rays(tr["datas"], tr["bi"], tr["ri"], tr["ci"], tr["init"].clone(), RATIO, tr["fids"],
+                            extra_points=tr["extra"])
+    mark(1)
+    loss.backward()
+    mark(2)
+    net.propagateTmpPsGrad(tr["fids"], RATIO)
+    mark(3)
+    nbytes = tr["ar"]()
+    mark(4)
+    opt.step()
+    mark(5)
+    return loss, nbytes
+
+
+def train_part(sc, dev, rank, world, dist, steps, warmup):
+    """-> dict for the JSON line (`train`): training rays/s of the whole job with the gradient all-reduce inside the
+    timed region, per-phase device times, the collective's own time / bytes, and the tensor roofline of the dominant
+    training kernel (weight-gradient GEMM of the def_regu block)."""
+    from selfreconcode_b200 import ops
+    tr = build_train(sc, dev, rank, world)
+    saved = [q.detach().clone() for q in tr["params"]]      # the scene is shared with the rendering / parity legs
+    for _ in range(max(warmup, 3)):
+        train_step(tr)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    phases, ar_ms, total = [], [], []
+    ops.LAUNCHES = 0
+    for _ in range(steps):
+        e = [ev() for _ in range(6)]
+        loss, nbytes = train_step(tr, e)
+        torch.cuda.synchronize()
+        phases.append([e[i].elapsed_time(e[i + 1]) for i in range(5)])
+        total.append(e[0].elapsed_time(e[5]))
+        ar_ms.append(tr["ar"].collective_ms())
+    info = dict(tr["net"].info)
+    t = torch.tensor([float(np.mean(total))], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    ph = np.mean(np.array(phases), axis=0)
+    with torch.no_grad():
+        for q, v in zip(tr["params"], saved):
+            q.copy_(v)
+    return {"metric": "training_rays_per_sec", "value": TRAIN_RAYS * world / (ms * 1e-3), "unit": "rays/s",
+            "ms_per_step": ms, "frames_per_gpu": TRAIN_FRAMES, "rays_per_gpu": TRAIN_RAYS,
+            "rays_converged": int(info["rayInfo"][1]),
+            "ms_forward_incl_trace": float(ph[0]), "ms_backward": float(ph[1]), "ms_propagate": float(ph[2]),
+            "ms_allreduce_incl_flatten": float(ph[3]), "ms_optimizer": float(ph[4]),
+            "allreduce": {"collective_ms": float(np.mean(ar_ms)), "bytes": int(nbytes), "op": "one NCCL all-reduce "
+                          "(sum, then /world) of every gradient: MLPs + per-frame poses / trans / latent codes"},
+            "loss": float(loss.item()), "losses": {k: float(v) for k, v in info.items() if k.endswith("_loss")},
+            "workload": "config[2]/[3] shape: %d frames of 512x512 per GPU, %d sampled silhouette rays, LBS + FastMinv, "
+                        "eikonal + colour + normal (weighted) + def_regu (device singular values) + offset losses, "
+                        "propagateTmpPsGrad, Adam; frames sharded across ranks (weak scaling)" % (TRAIN_FRAMES, TRAIN_RAYS)}
+
+
+def wgrad_roofline(dev, M=98304 * 4):
+    """Dominant training kernel timed alone: the 512x512 weight-gradient GEMM over the def_regu block's rows
+    (4 frames x 2 x 12 288 points x 4 rows), CUDA events on the launching stream, 3 MMAs per product."""
+    import ctypes as C
+    from selfreconcode_b200 import ops, _lib
+    lib = _lib.load()
+    g = torch.Generator(device=dev).manual_seed(5)
+    D = ops.tc_pack_rows(torch.randn(M, 512, device=dev, generator=g))
+    X = ops.tc_pack_rows(torch.randn(M, 512, device=dev, generator=g))
+    part = torch.empty((lib.sr_tc_wgrad_partial_bytes(M, 512, 512, None),), dtype=torch.uint8, device=dev)
+    dW = torch.empty(512, 512, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    for _ in range(3):
+        lib.sr_tc_wgrad(vp(D), 512, vp(X), 512, M, vp(part), vp(dW), 512, 512, 512, st)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        lib.sr_tc_wgrad(vp(D), 512, vp(X), 512, M, vp(part), vp(dW), 512, 512, 512, st)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    return ms, 2.0 * M * 512 * 512
+
+
+# --------------------------------------------------------------------------------------------------
 def cpu_reference_sample(n_rays, threads, seed=0, with_mc=True, rays=None, keep=False):
     """The oracle (CPU port of the reference path) on a bounded sample of the same workload.
     `rays` = the GPU arm's own ray set (CPU tensors): same inputs, so `keep=True` results can be compared
@@ -383,6 +515,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step section")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -508,6 +641,12 @@ def main():
     h2d = rays_h.numel() * 4 + init_h.numel() * 4 + bi_h.numel() * 8
     d2h = rgb_h.numel() * 4 + conv_h.numel()
 
+    train = None
+    if not args.no_train:
+        train = train_part(sc, dev, rank, world, dist, max(2, min(args.steps, 10)), args.warmup)
+        train_launches = ops.LAUNCHES
+        # the scene's parameters moved (Adam): nothing below depends on their values
+
     t_ray = torch.tensor([float(np.mean(ray_ms)), float(np.mean(mc_ms)), float(np.mean(e2e_ms)),
                           float(n_rays)], device=dev, dtype=torch.float64)
     if dist is not None:
@@ -570,6 +709,16 @@ def main():
         "clocks": clk.summary(),
         "wall_s_timed_region": t_wall,
     }
+    if train is not None:
+        wg_ms, wg_flops = wgrad_roofline(dev)
+        wg_tf = wg_flops / (wg_ms * 1e-3) / 1e12
+        train["gpu_launches_own_kernels_per_step"] = int(train_launches // max(2, min(args.steps, 10)))
+        train["roofline"] = {"kernel": "tc_wgrad_kernel (tcgen05 MN-major split-BF16 GEMM dW = delta^T x, 512x512 over "
+                                       "393 216 rows: the def_regu block's translator layers)", "bound": "tensor",
+                             "achieved": wg_tf, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": wg_tf / pk["tensor"],
+                             "ms_per_launch": wg_ms, "mma_terms": 3, "tensor_pipe_frac": 3.0 * wg_tf / pk["tensor"],
+                             "traffic": None, "peak_source": pk["src"] + " bf16 cuBLAS burst"}
+        line["train"] = train
     if not args.no_cpu_baseline and world == 1:
         threads = pick_threads()
         cb = cpu_reference_sample(None, threads, with_mc=True, rays={k: v for k, v in R.items()}, keep=True)

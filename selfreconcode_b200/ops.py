@@ -168,6 +168,26 @@ def marching_cubes(sdfs, xstep=1.0, ystep=1.0, zstep=1.0, xmin=0.0, ymin=0.0, zm
     return verts, faces
 
 
+def marching_cubes_count(sdfs, iso=0.0):
+    """(number of vertices, number of faces) marching_cubes() would produce: the classification + scan half of
+    the sweep only (used by the slab-sharded extraction to split a slab's output into own / halo parts)."""
+    _need_cuda(sdfs)
+    nx, ny, nz = sdfs.shape
+    lib = _lib.load()
+    dev = sdfs.device
+    with torch.cuda.device(dev):
+        wb = lib.sr_mc_work_bytes(nx, ny, nz)
+        key = (dev.index, torch.cuda.current_stream().cuda_stream, "count")
+        work = _mc_work.get(key)
+        if work is None or work.numel() < wb:
+            work = torch.empty((wb,), dtype=torch.uint8, device=dev)
+            _mc_work[key] = work
+        counts = torch.empty((2,), dtype=torch.int32, device=dev)
+        check(lib.sr_mc_count(_p(sdfs), nx, ny, nz, float(iso), _p(work), _p(counts), _stream()), "mc_count")
+        nv, nf = counts.tolist()
+    return nv, nf
+
+
 # ------------------------------------------------------------------------------------------------
 # interp2x_boundary  (MCAcc/cuda/interp2x_boundary3d.cpp:17-36)
 # ------------------------------------------------------------------------------------------------

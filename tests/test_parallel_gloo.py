@@ -71,6 +71,16 @@ def _worker(rank, world, port, q):
         v1, f1 = mc_fn(sdf, step, org, 0.0, 0)
         assert torch.equal(f, f1), "stitched faces identical to the single-device canonical mesh"
         assert torch.equal(v, v1)
+        # one emit pass + a count-only pass for the own / halo split; pieces gathered (unpadded) on rank 0 only
+        def count_fn(s_, iso):
+            a, b = mc_fn(s_, step, org, iso, 0)
+            return a.shape[0], b.shape[0]
+        v2, f2 = parallel.sharded_marching_cubes(sdf, step, org, 0.0, rank, world, mc_fn=mc_fn, count_fn=count_fn,
+                                                 gather_to=0)
+        if rank == 0:
+            assert torch.equal(f2, f1) and torch.equal(v2, v1)
+        else:
+            assert v2.shape == (0, 3) and f2.shape == (0, 3)
     dist.barrier()
     dist.destroy_process_group()
     q.put((rank, "ok"))
