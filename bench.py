@@ -201,6 +201,99 @@ def ray_part_api(sc, rays, init, bi):
 
 
 # --------------------------------------------------------------------------------------------------
+# BASELINE configs[0]: the reference's own CPU-runnable case -- one 128x128 frame, 4-layer / 64-wide SDF, identity
+# deformer, 65^3 (64^3 cells) coarse-to-fine grid + MC.  Small enough that the oracle runs the WHOLE case in about a
+# second, so the GPU arm and the CPU arm are timed and compared on identical inputs inside the default bench run.
+def config0_part(dev, threads):
+    from selfreconcode_b200 import synth, ops, enable_dropin
+    from oracle import oracle as O
+    from oracle import c_api
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    enable_dropin()
+    from MCAcc import Seg3dLossless
+    import MCGpu
+    torch.set_num_threads(threads)
+    sdf = synth.make_sdf(seed=40, hidden=64, n_hidden=4, feat=0, skip_in=(), perturb=0.0, bias=0.4)   # r in [0.37, 1.02]
+    cam = synth.camera(128, 128)
+    sp = helpers.sdf_params(sdf)
+    sdf_fn = lambda p: O.sdf_forward(sp, p, 6, 1.0, skip_in=())[0]
+    ident = lambda p, b: p
+    with torch.no_grad():
+        rays = synth.make_rays(cam, 1, lambda p: sdf_fn(p).view(-1), ident, seed=3, jitter=1e-3)
+    ang = synth.ang_threshold(cam, 0.5)
+    n = rays["rays"].shape[0]
+    # ---- CPU arm (oracle = the reference's algorithm on host cores), whole case
+    sens = {"eps_f": 5e-6, "eps_a": 2e-4}
+    t0 = time.perf_counter()
+    po, co, _ = O.optimize_surface_ps(cam["cam_pos"], rays["rays"], rays["init_pts"], rays["batch_inds"], sdf_fn, ident,
+                                      5e-5, ang, 3.05, 1.0, 10, sensitivity=sens)
+    t_ray_cpu = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        grid_o, calc_o = O.seg3d_forward(lambda q: sdf_fn(q).view(-1), [-1.2] * 3, [1.2] * 3, synth.MC_LADDER_65, 0.0)
+    spc, org = O.mc_world_params([-1.2] * 3, [1.2] * 3, (65, 65, 65))
+    vo, fo = c_api.marching_cubes(grid_o.permute(2, 1, 0).contiguous().numpy(), helpers.mc_tri_table(), 0.0, spc, org)
+    t_mc_cpu = time.perf_counter() - t0
+    # ---- GPU arm
+    sdf_d = sdf.to(dev)
+    net = sdf_d.fused()
+    net.set_pe_weights([1.0] * 6)
+    r_d, i_d, b_d = rays["rays"].to(dev), rays["init_pts"].to(dev), rays["batch_inds"].to(dev)
+    cp = cam["cam_pos"].to(dev)
+    eng = Seg3dLossless(query_func=lambda points: sdf_d.forward_fused(points.reshape(-1, 3), 1.0, False, False)[0]
+                        .reshape(1, 1, -1), b_min=[-1.2] * 3, b_max=[1.2] * 3, resolutions=synth.MC_LADDER_65,
+                        align_corners=False, balance_value=0.0, use_cuda_impl=True).to(dev)
+
+    def gpu_rays():
+        return ops.trace_surface_points(net, None, None, cp, r_d, i_d, b_d, None, 5e-5, ang, 3.05, 1.0, 10, mode="reverse")
+
+    def gpu_mc():
+        g = eng.forward()
+        v, f = MCGpu.mc_gpu(g[0, 0].permute(2, 1, 0).contiguous(), eng.spacing_x, eng.spacing_y, eng.spacing_z, eng.bx,
+                            eng.by, eng.bz, 0.0)
+        return g, v, f
+
+    for _ in range(3):
+        gpu_rays()
+        gpu_mc()
+    torch.cuda.synchronize()
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    tr, tm = [], []
+    for _ in range(5):
+        a, b, c = ev(), ev(), ev()
+        a.record()
+        pg, cg = gpu_rays()
+        b.record()
+        g, vg, fg = gpu_mc()
+        c.record()
+        torch.cuda.synchronize()
+        tr.append(a.elapsed_time(b))
+        tm.append(b.elapsed_time(c))
+    ok = ~sens["sensitive"].numpy()
+    dp = np.abs(pg.cpu().numpy() - po.numpy()).max(1)
+    mm = cg.cpu().numpy() != co.numpy()
+    gg, gc = g[0, 0].cpu().numpy(), grid_o.numpy()
+    sm = (gg > 0) != (gc > 0)
+    return {"workload": "config[0]: one 128x128 frame (%d silhouette rays), 4x64 SDF, identity deformer, trace times=10, "
+                        "65^3 coarse-to-fine grid + MC" % n,
+            "gpu": {"rays_per_sec": n / (float(np.mean(tr)) * 1e-3), "ms_rays": float(np.mean(tr)),
+                    "mc_voxels_per_sec": 65 ** 3 / (float(np.mean(tm)) * 1e-3), "ms_mc": float(np.mean(tm)),
+                    "engine": "fused fp32 FFMA (templated on width 64 / no skip / identity deformer)"},
+            "cpu_reference": {"rays_per_sec": n / t_ray_cpu, "mc_voxels_per_sec": 65 ** 3 / t_mc_cpu, "cores": threads,
+                              "kind": "port"},
+            "parity": {"rays": int(n), "rays_decision_sensitive": int((~ok).sum()),
+                       "conv_mismatch_insensitive": int((mm & ok).sum()), "conv_mismatch_all": int(mm.sum()),
+                       "pts_max_abs_err_insensitive": float(dp[ok].max()) if ok.any() else 0.0,
+                       "queried_gpu": int(eng.last_num_queried), "queried_oracle": int(calc_o.sum()),
+                       "sign_mismatch": int(sm.sum()),
+                       "sign_mismatch_outside_fp32_band": int((sm & (np.abs(gc) >= 1e-5)).sum()),
+                       "mc_faces_gpu": int(fg.shape[0]), "mc_faces_oracle": int(fo.shape[0]),
+                       "mc_mesh_identical": bool(fg.shape[0] == fo.shape[0] and np.array_equal(fg.cpu().numpy(), fo) and
+                                                 np.abs(vg.cpu().numpy() - vo).max() < 1e-5)}}
+
+
+# --------------------------------------------------------------------------------------------------
 # Training step (BASELINE configs[2] / [3]): batch of 4 frames per GPU, SMPL LBS + FastMinv on, eikonal + colour +
 # normal + def_regu + offset losses (config.conf loss_coarse), implicit differentiation, ONE NCCL all-reduce of all
 # gradients, Adam step -- train.py:160-171 with the per-point work on the tensor-core training engine.
@@ -224,9 +317,38 @@ def build_train(sc, dev, rank, world):
                                lambda p, b: comp.forward_fused(p.to(dev), [dcond, [poses, trans]], b.to(dev), RATIO)[0],
                                seed=31 + rank, jitter=3e-4)
     g = torch.Generator().manual_seed(77 + rank)
-    sel = torch.randperm(rays["rays"].shape[0], generator=g)[:TRAIN_RAYS].sort()[0]
+    sel = torch.randperm(rays["rays"].shape[0], generator=g)[:int(TRAIN_RAYS * 1.3)].sort()[0]
     f, pp, R, T, _, _ = data.get_camera_parameters(TRAIN_FRAMES, dev)
     cams = RectifiedPerspectiveCameras(f.detach(), pp.detach(), R, T.detach(), image_size=[(W, H)])
+    # The seed of the real pipeline (rasterised deformed template, network.py:485-493) puts D(start) on the PIXEL's own
+    # ray.  Setup-only stand-in: Gauss-Newton on {f(p) = 0, (D(p) - c) x v_pixel = 0} from the synthetic surface point,
+    # on top of the fused value / gradient / Jacobian kernels; rays that settle are kept, starts are jittered by 2e-4.
+    bi_a, ri_a, ci_a = rays["batch_inds"][sel].to(dev), rays["rows"][sel].to(dev), rays["cols"][sel].to(dev)
+    pix = torch.stack([ci_a, ri_a, torch.ones_like(ci_a)], dim=1).float()
+    dc = [dcond.detach(), [poses.detach(), trans.detach()]]
+    with torch.no_grad():
+        v = cams.view_rays(pix)
+        c = cams.cam_pos().view(1, 3)
+        p = rays["pstar"][sel].to(dev).clone()
+        vx = torch.zeros(p.shape[0], 3, 3, device=dev)
+        vx[:, 0, 1], vx[:, 0, 2], vx[:, 1, 0] = -v[:, 2], v[:, 1], v[:, 2]
+        vx[:, 1, 2], vx[:, 2, 0], vx[:, 2, 1] = -v[:, 0], -v[:, 1], v[:, 0]
+        for _ in range(12):
+            fv, gf, _ = sdf.forward_fused(p, RATIO, want_grad=True, want_feat=False)
+            d, J, _ = comp.forward_fused(p, dc, bi_a, RATIO, want_jac=True)
+            res = torch.cat([fv.view(-1, 1), torch.linalg.cross(v, d - c, dim=1)], dim=1)
+            B = torch.cat([gf.view(-1, 1, 3), vx @ J], dim=1)
+            step = torch.linalg.solve(B.transpose(1, 2) @ B + 1e-9 * torch.eye(3, device=dev), B.transpose(1, 2) @ res.unsqueeze(-1))
+            p = p - step.squeeze(-1).clamp(-0.05, 0.05)
+        fv = sdf.forward_fused(p, RATIO, False, False)[0].view(-1)
+        d = comp.forward_fused(p, dc, bi_a, RATIO)[0]
+        u = d - c
+        ang = torch.asin(torch.linalg.cross(u, v, dim=1).norm(dim=1) / u.norm(dim=1)) * 180.0 / np.pi
+        ok = (fv.abs() < 2e-5) & (ang < 0.3 * synth.ang_threshold(sc["cam"], 0.5))
+    keep = torch.nonzero(ok).view(-1)[:TRAIN_RAYS]
+    assert keep.numel() > 0.6 * TRAIN_RAYS, "seed solve settled on %d of %d rays" % (keep.numel(), TRAIN_RAYS)
+    jit = 2e-4 * torch.randn(keep.numel(), 3, generator=g).to(dev)
+    seeds = dict(bi=bi_a[keep], ri=ri_a[keep], ci=ci_a[keep], init=p[keep] + jit)
     holder = types.SimpleNamespace(rasterizer=types.SimpleNamespace(cameras=cams))
     conf = synth.reference_config().get_config("loss_coarse")
     net = OptimNetwork(sdf, comp, None, holder, rn, conf=conf)
@@ -239,8 +361,7 @@ def build_train(sc, dev, rank, world):
     nrm = torch.nn.functional.normalize(torch.randn(TRAIN_FRAMES, H, W, 3, generator=g), dim=-1).to(dev)
     extra = rays["pstar"][torch.randperm(rays["pstar"].shape[0], generator=g)[:4096]].to(dev)
     return dict(net=net, opt=opt, ar=ar, fids=fids, datas={"img": img, "normal": nrm}, extra=extra, params=params,
-                bi=rays["batch_inds"][sel].to(dev), ri=rays["rows"][sel].to(dev), ci=rays["cols"][sel].to(dev),
-                init=rays["init_pts"][sel].to(dev))
+                n_rays=int(keep.numel()), **seeds)
 
 
 def train_step(tr, events=None):
@@ -293,8 +414,11 @@ def train_part(sc, dev, rank, world, dist, steps, warmup):
     with torch.no_grad():
         for q, v in zip(tr["params"], saved):
             q.copy_(v)
-    return {"metric": "training_rays_per_sec", "value": TRAIN_RAYS * world / (ms * 1e-3), "unit": "rays/s",
-            "ms_per_step": ms, "frames_per_gpu": TRAIN_FRAMES, "rays_per_gpu": TRAIN_RAYS,
+    nr = torch.tensor([float(tr["n_rays"])], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(nr)
+    return {"metric": "training_rays_per_sec", "value": nr.item() / (ms * 1e-3), "unit": "rays/s",
+            "ms_per_step": ms, "frames_per_gpu": TRAIN_FRAMES, "rays_per_gpu": tr["n_rays"],
             "rays_converged": int(info["rayInfo"][1]),
             "ms_forward_incl_trace": float(ph[0]), "ms_backward": float(ph[1]), "ms_propagate": float(ph[2]),
             "ms_allreduce_incl_flatten": float(ph[3]), "ms_optimizer": float(ph[4]),
@@ -732,6 +856,7 @@ def main():
         line["parity"] = parity_report(dict(pts=pts_g, conv=conv_g, rgb=rgb_g, grid=grid_g[0, 0],
                                             calc=eng.last_calculated, verts=v_g, faces=f_g,
                                             verts_on_oracle_grid=v_o, faces_on_oracle_grid=f_o), cb["keep"])
+        line["config0"] = config0_part(dev, threads)
         line["cpu_baseline"] = {"value": cb["rays_per_sec"], "unit": "rays/s", "cores": threads, "kind": "port",
                                 "sample": "all rays of the same frame (trace times=10 + shading) and the same 257^3 "
                                           "coarse-to-fine grid + MC through oracle/ (torch fp32 CPU + C)",
