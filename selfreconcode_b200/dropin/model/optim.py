@@ -523,7 +523,17 @@ class OptimNetwork(nn.Module):
         self.TmpOptimizer.zero_grad()
         loss.backward()
         self.TmpOptimizer.step()
-        sdf_loss = (self._sdf_value(self.TmpVs, ratio).view(-1) + self.sdfShrinkRadius).abs().mean()
+        pred = self._sdf_value(self.TmpVs, ratio).view(-1) + self.sdfShrinkRadius
+        if utils.train_fused(self.deformer, self.sdf):
+            # d|x|/dx = sign(x) is a DECISION on values that sit on the zero set by construction (template vertices):
+            # it is taken on the fp32 engine's value (tensor-core values inside their error band are re-evaluated,
+            # ops.sdf_refine_band), then applied to the differentiable tensor-core evaluation
+            with torch.no_grad():
+                f32 = self.sdf.forward_fused(self.TmpVs.detach(), ratio, False, False,
+                                             refine_about=-self.sdfShrinkRadius)[0].view(-1) + self.sdfShrinkRadius
+            sdf_loss = (torch.sign(f32) * pred).mean()
+        else:
+            sdf_loss = pred.abs().mean()
         self.info['pc_loss_sdf'] = sdf_loss.item()
         return sdf_loss * (conf.get_float('pc_weight.weight') if has_pc else 60.)
 

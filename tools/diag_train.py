@@ -73,6 +73,53 @@ def main():
             print("want_feat=%s  %-48s dL/dp %.1e  worst param %s %.1e  per layer v: %s"
                   % (want_feat, name, ep, worst[0], worst[1],
                      " ".join("%.0e" % e for k, e in errs if k.endswith("weight_v"))))
+    # value-only sweeps (1 row per point), as the template-vertex term |f(TmpVs)| and the implicit-differentiation VJP use
+    def ref_f(sdf, p):
+        from selfreconcode_b200 import train_ops as T
+        x0 = T.embed_rows(p, 6, [1.0] * 6, 1, ld=39)
+        x = x0
+        L = sdf.num_layers - 1
+        for l in range(L):
+            lin = getattr(sdf, "lin%d" % l)
+            W = lin.weight_v * (lin.weight_g.view(-1, 1) / lin.weight_v.norm(dim=1, keepdim=True))
+            if l in sdf.skip_in:
+                x = torch.cat([x, x0], 1) / np.sqrt(2)
+            x = x @ W.t() + lin.bias
+            if l < L - 1:
+                x = torch.nn.functional.softplus(x, beta=100)
+        return x[:, :1]
+
+    for npts in (pts.shape[0], 2472, 174, 3614):
+        pp = torch.cat([pts] * 4)[:npts]
+        cot = torch.randn(npts, 1, device=dev)
+        for name, fn in (("mean |f|", lambda f: f.abs().mean()), ("VJP random cot", lambda f: (f * cot.to(f.dtype)).sum())):
+            sdf32.zero_grad()
+            sdf64.zero_grad()
+            p32 = pp.clone().requires_grad_(True)
+            fn(sdf32.forward_train(p32, 1.0, want_grad=False, want_feat=False)[0]).backward()
+            p64 = pp.double().clone().requires_grad_(True)
+            fn(ref_f(sdf64, p64)).backward()
+            errs = [(k, norm_err(a.grad.cpu().numpy(), b.grad.cpu().numpy()))
+                    for (k, a), (_, b) in zip(sdf32.named_parameters(), sdf64.named_parameters())
+                    if b.grad is not None and float(b.grad.abs().max()) > 0]
+            worst = max(errs, key=lambda kv: kv[1])
+            print("1 row/pt, %5d pts  %-16s dL/dp %.1e  worst %s %.1e  v: %s" % (
+                npts, name, norm_err(p32.grad.cpu().numpy(), p64.grad.cpu().numpy()), worst[0], worst[1],
+                " ".join("%.0e" % e for k, e in errs if k.endswith("weight_v"))))
+    # 4 rows/pt with an odd number of row tiles (3614 points -> 113 tiles)
+    pp = torch.cat([pts] * 4)[:3614]
+    sdf32.zero_grad()
+    sdf64.zero_grad()
+    p32 = pp.clone().requires_grad_(True)
+    eik = lambda gf: ((gf.norm(2, dim=-1) - 1) ** 2).mean()
+    eik(sdf32.forward_train(p32, 1.0, True, False)[1]).backward()
+    p64 = pp.double().clone().requires_grad_(True)
+    eik(ref_forward4(sdf64, p64)[1]).backward()
+    errs = [(k, norm_err(a.grad.cpu().numpy(), b.grad.cpu().numpy()))
+            for (k, a), (_, b) in zip(sdf32.named_parameters(), sdf64.named_parameters())
+            if b.grad is not None and float(b.grad.abs().max()) > 0]
+    print("eikonal, 3614 pts (113 row tiles): dL/dp %.1e  v: %s" % (
+        norm_err(p32.grad.cpu().numpy(), p64.grad.cpu().numpy()), " ".join("%.0e" % e for k, e in errs if k.endswith("weight_v"))))
     # forward accuracy by row type
     with torch.no_grad():
         f, gf, ft = sdf32.forward_train(pts, 1.0, True, True)
