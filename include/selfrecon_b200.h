@@ -325,6 +325,27 @@ int sr_tc_wgrad(const void* D, int Kd, const void* X, int Kx, int64_t M, float* 
 int sr_tc_colsum(const void* T, int64_t M, int K, int ch, float* partial, int slices, cudaStream_t s);
 int sr_tc_unpack_rows(const void* T, int64_t M, int K, int Kpad, float* out, int ld, cudaStream_t s);
 
+/* Whole-sweep entry points: all launches of one forward / backward evaluation of an MLP from ONE call (per-layer
+ * operands = the module's persistent packs).  forward: x0 [M, ld] fp32 rows -> out [M, n_last]; keeps the input tiles
+ * (A_in), every hidden layer's activation tiles (acts[i], sr_tc_act_bytes(M, k_{i+1})) and, for softplus layers, the fp32
+ * act'(z) (stashes[i] [M, pad256(n_i)] or NULL).  backward: gout [M, n_last] -> dW[l] [n,k] / db[l] [n] (NULL entries are
+ * skipped) and x0_grad [M, ld] (or NULL); D0 / D1 = two delta tile buffers of sr_tc_act_bytes(M, widest layer),
+ * part = sr_tc_wgrad_partial_bytes scratch for the widest pair, colsum_ws = colsum_slices x widest floats,
+ * g_skip [M, g_skip_ld] scratch when a layer has a skip connection. */
+typedef struct sr_tc_layer {
+  const void* W;          /* packed weights, forward orientation (sr_tc_pack_weights of [n,k]) */
+  const void* Wb;         /* packed W^T ([k,n]) for the reverse launch */
+  const float* bias;      /* padded to a multiple of 256 */
+  const float* zero_bias; /* zeros, pad256(k) */
+  int n, k, act, skip;
+} sr_tc_layer;
+int sr_tc_mlp_forward(const sr_tc_layer* layers, int L, const float* x0, int64_t M, int ld, int d_in, int ch, void* A_in,
+                      void* const* acts, float* const* stashes, float* out, cudaStream_t s);
+int sr_tc_mlp_backward(const sr_tc_layer* layers, int L, int64_t M, int ld, int d_in, int ch, const float* gout,
+                       const void* A_in, void* const* acts, float* const* stashes, void* D0, void* D1, float* part,
+                       float* colsum_ws, int colsum_slices, float* const* dW, float* const* db, float* x0_grad,
+                       float* g_skip, int g_skip_ld, cudaStream_t s);
+
 /* Batched 3x3 singular values (descending) + right singular vectors (columns of V, may be NULL), and the
  * backward of a function of the VALUES: gJ = sum_i gS_i u_i v_i^T.  Replaces `torch.svd(Jacobs.cpu())` of the
  * def_regu block (model/network.py:573-575).  J, V, gJ: [n,3,3] row-major; S, gS: [n,3]. */

@@ -40,6 +40,11 @@ class LbsParams(C.Structure):
                 ("trans", C.c_void_p), ("F", C.c_int)]
 
 
+class TcLayer(C.Structure):
+    _fields_ = [("W", C.c_void_p), ("Wb", C.c_void_p), ("bias", C.c_void_p), ("zero_bias", C.c_void_p),
+                ("n", C.c_int), ("k", C.c_int), ("act", C.c_int), ("skip", C.c_int)]
+
+
 class TraceParams(C.Structure):
     _fields_ = [("cam_pos", C.c_float * 3), ("dthreshold", C.c_float), ("athreshold", C.c_float),
                 ("w1", C.c_float), ("w2", C.c_float)]
@@ -107,6 +112,11 @@ SIGNATURES = {
     "sr_raster_mesh": (C.c_int, [c_f, c_f, i64, i64, i64, i32, i32, c_f, c_f, c_f, c_f, stream_t]),
     "sr_tc_wgrad_partial_bytes": (i64, [i64, i32, i32, C.POINTER(C.c_int)]),
     "sr_tc_debug_wgrad_desc_swap": (None, [i32]),
+    "sr_tc_mlp_forward": (C.c_int, [C.POINTER(TcLayer), i32, c_f, i64, i32, i32, i32, c_f, C.POINTER(C.c_void_p),
+                                    C.POINTER(C.c_void_p), c_f, stream_t]),
+    "sr_tc_mlp_backward": (C.c_int, [C.POINTER(TcLayer), i32, i64, i32, i32, i32, c_f, c_f, C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_void_p), c_f, c_f, c_f, c_f, i32, C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_void_p), c_f, c_f, i32, stream_t]),
     "sr_tc_wgrad": (C.c_int, [c_f, i32, c_f, i32, i64, c_f, c_f, i32, i32, i32, stream_t]),
     "sr_tc_colsum": (C.c_int, [c_f, i64, i32, i32, c_f, i32, stream_t]),
     "sr_tc_unpack_rows": (C.c_int, [c_f, i64, i32, i32, c_f, i32, stream_t]),

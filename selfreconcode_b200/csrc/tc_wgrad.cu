@@ -326,3 +326,125 @@ int sr_tc_unpack_rows(const void* T, int64_t M, int K, int Kpad, float* out, int
   return sr_launch_status();
 }
 }
+
+// ---- whole-sweep entry points ---------------------------------------------------------------------
+// One C call per forward / backward sweep of an MLP: the per-layer launches above are issued from here, so the host
+// cost of a training evaluation is one FFI crossing instead of ~5 per layer (the 8192-ray training step was bound by
+// Python launch overhead: ~700 own launches per step).
+namespace sr_tc {
+
+__global__ void colsum_reduce_kernel(const float* __restrict__ partial, int slices, int ld, float* __restrict__ out, int n) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  float acc = 0.f;
+  for (int s = 0; s < slices; ++s) acc += partial[(size_t)s * ld + k];
+  out[k] = acc;
+}
+
+__global__ void add_cols_kernel(float* __restrict__ dst, int ld_dst, const float* __restrict__ src, int ld_src, long long M,
+                                int n) {
+  const long long total = M * n;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / n;
+    const int c = (int)(idx % n);
+    dst[r * ld_dst + c] += src[r * ld_src + c];
+  }
+}
+
+__global__ void zero_cols_kernel(float* __restrict__ dst, int ld, long long M, int c0, int c1) {
+  const int w = c1 - c0;
+  const long long total = M * w;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x)
+    dst[(idx / w) * ld + c0 + (int)(idx % w)] = 0.f;
+}
+
+}  // namespace sr_tc
+
+extern "C" {
+
+int sr_tc_linear(const void* A, const void* W, const float* bias, int64_t M, int N, int K, int n_valid, int act, int ch,
+                 void* A_next, int K_next, float scale, const float* skip_src, int skip_n, int skip_ld, float* out,
+                 int out_ld, int out_col0, int out_n, float* dstash, const void* mul_tiles, int mul_K, int mul_act,
+                 float mul_scale, const int32_t* m_dev, cudaStream_t s);
+int sr_tc_pack_rows(const float* src, int64_t M, int K, int ld, void* dst, const int32_t* m_dev, cudaStream_t s);
+
+static inline int pad_to(int x, int m) { return (x + m - 1) / m * m; }
+
+int sr_tc_mlp_forward(const sr_tc_layer* layers, int L, const float* x0, int64_t M, int ld, int d_in, int ch, void* A_in,
+                      void* const* acts, float* const* stashes, float* out, cudaStream_t s) {
+  if (!layers || L <= 0 || L > 16 || !x0 || M <= 0 || ld <= 0 || (ld % 32) != 0 || !A_in || !out || (L > 1 && !acts))
+    return SR_EINVAL;
+  int rc = sr_tc_pack_rows(x0, M, ld, ld, A_in, nullptr, s);
+  if (rc) return rc;
+  const void* cur = A_in;
+  int K = ld;
+  for (int i = 0; i < L; ++i) {
+    const sr_tc_layer& ly = layers[i];
+    const bool last = i == L - 1;
+    const bool skip_next = !last && layers[i + 1].skip;
+    const int Kn = last ? 0 : pad_to(layers[i + 1].k, 32);
+    rc = sr_tc_linear(cur, ly.W, ly.bias, M, ly.n, K, ly.n, ly.act, ch, last ? nullptr : acts[i], Kn,
+                      skip_next ? 0.70710678118654752f : 1.0f, skip_next ? x0 : nullptr, skip_next ? d_in : 0, ld,
+                      last ? out : nullptr, last ? ly.n : 0, 0, ly.n, (!last && stashes) ? stashes[i] : nullptr, nullptr, 0,
+                      0, 1.0f, nullptr, s);
+    if (rc) return rc;
+    if (!last) { cur = acts[i]; K = Kn; }
+  }
+  return SR_OK;
+}
+
+int sr_tc_mlp_backward(const sr_tc_layer* layers, int L, int64_t M, int ld, int d_in, int ch, const float* gout,
+                       const void* A_in, void* const* acts, float* const* stashes, void* D0, void* D1, float* part,
+                       float* colsum_ws, int colsum_slices, float* const* dW, float* const* db, float* x0_grad,
+                       float* g_skip, int g_skip_ld, cudaStream_t s) {
+  using namespace sr_tc;
+  if (!layers || L <= 0 || L > 16 || M <= 0 || !gout || !A_in || !D0 || !D1 || !part || !colsum_ws || !dW || !db)
+    return SR_EINVAL;
+  const int n_last = layers[L - 1].n;
+  int Kd = pad_to(n_last, 32);
+  void* D = D0;
+  void* Dn = D1;
+  int rc = sr_tc_pack_rows(gout, M, n_last, n_last, D, nullptr, s);
+  if (rc) return rc;
+  bool had_skip = false;
+  for (int l = L - 1; l >= 0; --l) {
+    const sr_tc_layer& ly = layers[l];
+    const void* X = l > 0 ? acts[l - 1] : A_in;
+    const int Kx = l > 0 ? pad_to(ly.k, 32) : ld;
+    if (dW[l]) {
+      rc = sr_tc_wgrad(D, Kd, X, Kx, M, part, dW[l], ly.n, ly.k, ly.k, s);
+      if (rc) return rc;
+    }
+    if (db[l]) {
+      rc = sr_tc_colsum(D, M, Kd, ch, colsum_ws, colsum_slices, s);
+      if (rc) return rc;
+      colsum_reduce_kernel<<<(ly.n + 127) / 128, 128, 0, s>>>(colsum_ws, colsum_slices, Kd, db[l], ly.n);
+    }
+    if (l == 0 && !x0_grad) break;
+    const float scale = ly.skip ? 0.70710678118654752f : 1.0f;
+    if (l > 0) {
+      const int n_prev = layers[l - 1].n;
+      const int Kd_prev = pad_to(n_prev, 32);
+      if (ly.skip && !g_skip) return SR_EINVAL;
+      rc = sr_tc_linear(D, ly.Wb, ly.zero_bias, M, ly.k, Kd, n_prev, SR_ACT_NONE, ch, Dn, Kd_prev, scale, nullptr, 0, 0,
+                        ly.skip ? g_skip : nullptr, ly.skip ? g_skip_ld : 0, n_prev, ly.skip ? d_in : 0,
+                        stashes ? stashes[l - 1] : nullptr, acts[l - 1], pad_to(ly.k, 32), layers[l - 1].act, scale, nullptr,
+                        s);
+      if (rc) return rc;
+      had_skip |= ly.skip != 0;
+      void* t = D; D = Dn; Dn = t;
+      Kd = Kd_prev;
+    } else {
+      rc = sr_tc_linear(D, ly.Wb, ly.zero_bias, M, ly.k, Kd, ly.k, SR_ACT_NONE, 1, nullptr, 0, scale, nullptr, 0, 0, x0_grad,
+                        ld, 0, ly.k, nullptr, nullptr, 0, 0, 1.0f, nullptr, s);
+      if (rc) return rc;
+      if (ly.k < ld) zero_cols_kernel<<<sr_grid_for(M * (ld - ly.k), 256, 4), 256, 0, s>>>(x0_grad, ld, M, ly.k, ld);
+      if (had_skip)
+        add_cols_kernel<<<sr_grid_for(M * d_in, 256, 4), 256, 0, s>>>(x0_grad, ld, g_skip, g_skip_ld, M, d_in);
+    }
+  }
+  return sr_launch_status();
+}
+}

@@ -68,6 +68,57 @@ COLSUM_SLICES = 64
 DEBUG_LAST = None      # tests: set to a dict to receive the tiles kept by the last forward (acts, shapes)
 
 
+def _align(n, a=256):
+    return (n + a - 1) // a * a
+
+
+class _Arena:
+    """One device allocation carved into aligned pieces (activation tiles, stashes, scratch): a sweep costs one
+    torch.empty instead of one per layer."""
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.sizes = []
+
+    def add(self, nbytes):
+        off = sum(self.sizes)
+        self.sizes.append(_align(int(nbytes)))
+        return len(self.sizes) - 1, off
+
+    def alloc(self):
+        self.buf = torch.empty((max(sum(self.sizes), 1),), dtype=torch.uint8, device=self.dev)
+        self.base = self.buf.data_ptr()
+        return self
+
+    def ptr(self, off):
+        return self.base + off
+
+
+def _layer_array(lib, cfg, Ws, bs, dev):
+    """ctypes array of sr_tc_layer (+ the tensors that must stay alive): the module's persistent packs when given,
+    else packed here from the weight tensors."""
+    L = len(Ws)
+    arr = (_lib.TcLayer * L)()
+    keep = []
+    for i in range(L):
+        n, k = Ws[i].shape
+        pk = cfg.packs[i] if cfg.packs is not None else None
+        if pk is not None and (pk["n"], pk["k"]) == (n, k):
+            W, Wb, bias, zb = pk["W"], pk["Wb"], pk["bias"], pk["zero_bias"]
+        else:
+            W = _pack_weights(lib, Ws[i])
+            Wb = _pack_weights(lib, Ws[i].t().contiguous())          # [k rows, n cols]
+            bias = torch.zeros((_pad(n, 256),), dtype=torch.float32, device=dev)
+            if bs[i] is not None:
+                bias[:n] = bs[i].detach().float()
+            zb = torch.zeros((_pad(k, 256),), dtype=torch.float32, device=dev)
+        keep += [W, Wb, bias, zb]
+        a = arr[i]
+        a.W, a.Wb, a.bias, a.zero_bias = W.data_ptr(), Wb.data_ptr(), bias.data_ptr(), zb.data_ptr()
+        a.n, a.k, a.act, a.skip = n, k, cfg.acts[i], 1 if cfg.skips[i] else 0
+    return arr, keep
+
+
 class TcMlpFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x0, cfg, *wb):
@@ -82,113 +133,77 @@ class TcMlpFunction(torch.autograd.Function):
         bs = [wb[2 * i + 1] for i in range(L)]
         ch = cfg.ch
         with torch.cuda.device(dev):
-            A_in = torch.empty((lib.sr_tc_act_bytes(M, ld),), dtype=torch.uint8, device=dev)
-            check(lib.sr_tc_pack_rows(_p(x0), M, ld, ld, _p(A_in), None, _stream()), "tc_pack_rows")
-            packed, acts, stashes = [], [], []
-            cur, K = A_in, ld
-            out = None
-            for i in range(L):
-                n, k = Ws[i].shape
-                last = i == L - 1
-                pk = cfg.packs[i] if cfg.packs is not None else None
-                if pk is not None and (pk["n"], pk["k"]) == (n, k):
-                    Wp, bias = pk["W"], pk["bias"]
-                else:
-                    pk = None
-                    Wp = _pack_weights(lib, Ws[i])
-                    bias = torch.zeros((_pad(n, 256),), dtype=torch.float32, device=dev)
-                    if bs[i] is not None:
-                        bias[:n] = bs[i].detach().float()
-                packed.append(pk)
-                skip_next = (not last) and cfg.skips[i + 1]
-                Kn = 0 if last else _pad(Ws[i + 1].shape[1], 32)
-                A_next = None if last else torch.empty((lib.sr_tc_act_bytes(M, Kn),), dtype=torch.uint8, device=dev)
-                if last:
-                    out = torch.empty((M, n), dtype=torch.float32, device=dev)
-                # softplus(beta=100): keep act'(z) in fp32 for the reverse sweep (1 - act' recomputed from the
+            layers, keep = _layer_array(lib, cfg, Ws, bs, dev)
+            ar = _Arena(dev)
+            _, o_in = ar.add(lib.sr_tc_act_bytes(M, ld))
+            o_act, o_st = [], []
+            for i in range(L - 1):
+                o_act.append(ar.add(lib.sr_tc_act_bytes(M, _pad(Ws[i + 1].shape[1], 32)))[1])
+                # softplus(beta=100): act'(z) kept in fp32 for the reverse sweep (1 - act' recomputed from the
                 # 16-bit-mantissa activation tiles would carry 100 x 2^-17 of relative error into every gradient)
-                ds = torch.empty((M, _pad(n, 256)), dtype=torch.float32, device=dev) \
-                    if (not last and cfg.acts[i] == _lib.SR_ACT_SOFTPLUS100) else None
-                check(lib.sr_tc_linear(_p(cur), _p(Wp), _p(bias), M, n, K, n, cfg.acts[i], ch, _p(A_next), Kn,
-                                       INV_SQRT2 if skip_next else 1.0, _p(x0) if skip_next else None,
-                                       cfg.d_in if skip_next else 0, ld, _p(out), n if last else 0, 0, n, _p(ds), None,
-                                       0, 0, 1.0, None, _stream()), "tc_linear")
-                if not last:
-                    acts.append(A_next)
-                    stashes.append(ds)
-                    cur, K = A_next, Kn
+                o_st.append(ar.add(M * _pad(Ws[i].shape[0], 256) * 4)[1] if cfg.acts[i] == _lib.SR_ACT_SOFTPLUS100 else None)
+            ar.alloc()
+            acts = (C.c_void_p * max(L - 1, 1))(*[ar.ptr(o) for o in o_act])
+            stashes = (C.c_void_p * max(L - 1, 1))(*[ar.ptr(o) if o is not None else None for o in o_st])
+            out = torch.empty((M, Ws[-1].shape[0]), dtype=torch.float32, device=dev)
+            check(lib.sr_tc_mlp_forward(layers, L, _p(x0), M, ld, cfg.d_in, ch, C.c_void_p(ar.ptr(o_in)), acts, stashes,
+                                        _p(out), _stream()), "tc_mlp_forward")
+            ops.LAUNCHES += L      # check() counted one; a sweep is 1 + L launches
         ctx.cfg, ctx.M, ctx.ld, ctx.L = cfg, M, ld, L
-        ctx.A_in, ctx.acts, ctx.Ws, ctx.packed, ctx.stashes = A_in, acts, Ws, packed, stashes
+        ctx.arena, ctx.o_in, ctx.acts_c, ctx.stashes_c, ctx.o_act = ar, o_in, acts, stashes, o_act
+        ctx.layers, ctx.keep, ctx.shapes = layers, keep, [tuple(w.shape) for w in Ws]
         ctx.has_bias = [b is not None for b in bs]
         if DEBUG_LAST is not None:
-            DEBUG_LAST.update(acts=acts, M=M, widths=[w.shape[0] for w in Ws], kpads=[_pad(w.shape[1], 32) for w in Ws])
+            views = [ar.buf[o:o + lib.sr_tc_act_bytes(M, _pad(Ws[i + 1].shape[1], 32))] for i, o in enumerate(o_act)]
+            DEBUG_LAST.update(acts=views, M=M, widths=[w.shape[0] for w in Ws], kpads=[_pad(w.shape[1], 32) for w in Ws])
         return out
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, gout):
         lib = _lib.load()
-        cfg, M, ld, L, Ws = ctx.cfg, ctx.M, ctx.ld, ctx.L, ctx.Ws
+        cfg, M, ld, L, shapes = ctx.cfg, ctx.M, ctx.ld, ctx.L, ctx.shapes
         ch = cfg.ch
         dev = gout.device
         need_x0 = ctx.needs_input_grad[0]
-        grads = [None] * (2 * L)
         with torch.cuda.device(dev):
-            n_last = Ws[-1].shape[0]
-            Kd = _pad(n_last, 32)
             g = gout.detach().contiguous().float()
-            D = torch.empty((lib.sr_tc_act_bytes(M, Kd),), dtype=torch.uint8, device=dev)
-            check(lib.sr_tc_pack_rows(_p(g), M, n_last, n_last, _p(D), None, _stream()), "tc_pack_rows")
-            x0_grad = None
-            g_skip = None
-            for l in range(L - 1, -1, -1):
-                n, k = Ws[l].shape
-                X = ctx.acts[l - 1] if l > 0 else ctx.A_in
-                Kx = _pad(k, 32) if l > 0 else ld
-                # ---- weight / bias gradients from the kept tiles
-                if ctx.needs_input_grad[2 + 2 * l]:
-                    nbytes = lib.sr_tc_wgrad_partial_bytes(M, Kd, Kx, None)
-                    part = _Workspace.get(dev, nbytes)
-                    dW = torch.empty((n, k), dtype=torch.float32, device=dev)
-                    check(lib.sr_tc_wgrad(_p(D), Kd, _p(X), Kx, M, _p(part), _p(dW), n, k, k, _stream()), "tc_wgrad")
-                    grads[2 * l] = dW
-                if ctx.has_bias[l] and ctx.needs_input_grad[3 + 2 * l]:
-                    ps = torch.empty((COLSUM_SLICES, Kd), dtype=torch.float32, device=dev)
-                    check(lib.sr_tc_colsum(_p(D), M, Kd, ch, _p(ps), COLSUM_SLICES, _stream()), "tc_colsum")
-                    grads[2 * l + 1] = ps.sum(0)[:n]
-                if l == 0 and not need_x0:
-                    break
-                # ---- reverse GEMM: cotangent of this layer's input
-                pk = ctx.packed[l]
-                if pk is not None:
-                    Wt, zb = pk["Wb"], pk["zero_bias"]
-                else:
-                    Wt = _pack_weights(lib, Ws[l].t().contiguous())          # [k rows, n cols]
-                    zb = torch.zeros((_pad(k, 256),), dtype=torch.float32, device=dev)
-                scale = INV_SQRT2 if cfg.skips[l] else 1.0
-                if l > 0:
-                    n_prev = Ws[l - 1].shape[0]
-                    Kd_prev = _pad(n_prev, 32)
-                    D_prev = torch.empty((lib.sr_tc_act_bytes(M, Kd_prev),), dtype=torch.uint8, device=dev)
-                    if cfg.skips[l]:
-                        g_skip = torch.empty((M, _pad(cfg.d_in, 4)), dtype=torch.float32, device=dev)
-                    check(lib.sr_tc_linear(_p(D), _p(Wt), _p(zb), M, k, Kd, n_prev, SR_ACT_NONE, ch, _p(D_prev), Kd_prev,
-                                           scale, None, 0, 0, _p(g_skip) if cfg.skips[l] else None,
-                                           g_skip.shape[1] if cfg.skips[l] else 0, n_prev,
-                                           cfg.d_in if cfg.skips[l] else 0, _p(ctx.stashes[l - 1]), _p(ctx.acts[l - 1]),
-                                           _pad(k, 32),
-                                           cfg.acts[l - 1], scale, None, _stream()), "tc_linear")
-                    D, Kd = D_prev, Kd_prev
-                else:
-                    x0_grad = torch.empty((M, ld), dtype=torch.float32, device=dev)
-                    check(lib.sr_tc_linear(_p(D), _p(Wt), _p(zb), M, k, Kd, k, SR_ACT_NONE, 1, None, 0, scale, None, 0,
-                                           0, _p(x0_grad), ld, 0, k, None, None, 0, 0, 1.0, None, _stream()),
-                          "tc_linear")
-                    if k < ld:
-                        x0_grad[:, k:] = 0.0
-            if x0_grad is not None and g_skip is not None:
-                x0_grad[:, :cfg.d_in] += g_skip[:, :cfg.d_in]
-        ctx.acts = ctx.A_in = ctx.stashes = None
+            wmax = max(_pad(n, 32) for n, _ in shapes)
+            kmax = max([_pad(k, 32) for _, k in shapes[1:]] + [ld])
+            ar = _Arena(dev)
+            o_d0 = ar.add(lib.sr_tc_act_bytes(M, wmax))[1]
+            o_d1 = ar.add(lib.sr_tc_act_bytes(M, wmax))[1]
+            o_part = ar.add(lib.sr_tc_wgrad_partial_bytes(M, wmax, kmax, None))[1]
+            o_cs = ar.add(COLSUM_SLICES * wmax * 4)[1]
+            gs_ld = _pad(cfg.d_in, 4)
+            o_gs = ar.add(M * gs_ld * 4)[1] if any(cfg.skips) else None
+            ar.alloc()
+            # gradients: one buffer, handed back as views
+            sizes = [n * k for n, k in shapes] + [n for n, _ in shapes]
+            flat = torch.empty((sum(sizes),), dtype=torch.float32, device=dev)
+            dWs, dbs, o = [], [], 0
+            for n, k in shapes:
+                dWs.append(flat[o:o + n * k].view(n, k))
+                o += n * k
+            for n, _ in shapes:
+                dbs.append(flat[o:o + n])
+                o += n
+            want_w = [ctx.needs_input_grad[2 + 2 * l] for l in range(L)]
+            want_b = [ctx.has_bias[l] and ctx.needs_input_grad[3 + 2 * l] for l in range(L)]
+            dW_c = (C.c_void_p * L)(*[dWs[l].data_ptr() if want_w[l] else None for l in range(L)])
+            db_c = (C.c_void_p * L)(*[dbs[l].data_ptr() if want_b[l] else None for l in range(L)])
+            x0_grad = torch.empty((M, ld), dtype=torch.float32, device=dev) if need_x0 else None
+            fa = ctx.arena
+            check(lib.sr_tc_mlp_backward(ctx.layers, L, M, ld, cfg.d_in, ch, _p(g), C.c_void_p(fa.ptr(ctx.o_in)), ctx.acts_c,
+                                         ctx.stashes_c, C.c_void_p(ar.ptr(o_d0)), C.c_void_p(ar.ptr(o_d1)),
+                                         C.c_void_p(ar.ptr(o_part)), C.c_void_p(ar.ptr(o_cs)), COLSUM_SLICES, dW_c, db_c,
+                                         _p(x0_grad), C.c_void_p(ar.ptr(o_gs)) if o_gs is not None else None, gs_ld,
+                                         _stream()), "tc_mlp_backward")
+            ops.LAUNCHES += 5 * L
+        grads = []
+        for l in range(L):
+            grads += [dWs[l] if want_w[l] else None, dbs[l] if want_b[l] else None]
+        ctx.arena = ctx.keep = None
         return (x0_grad, None) + tuple(grads)
 
 
