@@ -288,6 +288,10 @@ int sr_tc_embed(const float* pts, int64_t P, int multires, const float* pe_w, in
                 const float* conds, const int64_t* batch_inds, int64_t pts_per_frame, int condlen,
                 float* out, int ld, const int32_t* index /* optional active list */,
                 const int32_t* m_dev /* optional device-side count */, cudaStream_t s);
+/* Backward of sr_tc_embed w.r.t. the points: gx [P*ch, ld] -> gp [P,3] (value row: d PE/dp; tangent rows: second
+ * derivative of the encoding).  The latent-code columns are a plain slice of gx (value rows). multires <= 8. */
+int sr_tc_embed_backward(const float* pts, int64_t P, int multires, const float* pe_w, int ch, const float* gx, int ld,
+                         float* gp, cudaStream_t s);
 int64_t sr_tc_act_bytes(int64_t M, int K);
 int64_t sr_tc_weight_bytes(int N, int K);
 int sr_tc_pack_rows(const float* src, int64_t M, int K, int ld, void* dst, const int32_t* m_dev,

@@ -98,6 +98,7 @@ SIGNATURES = {
                                     stream_t]),
     "sr_tc_embed": (C.c_int, [c_f, i64, i32, C.POINTER(f32), i32, c_f, c_f, i64, i32, c_f, i32, c_f, c_f,
                               stream_t]),
+    "sr_tc_embed_backward": (C.c_int, [c_f, i64, i32, C.POINTER(f32), i32, c_f, i32, c_f, stream_t]),
     "sr_tc_act_bytes": (i64, [i64, i32]),
     "sr_tc_weight_bytes": (i64, [i32, i32]),
     "sr_tc_pack_rows": (C.c_int, [c_f, i64, i32, i32, c_f, c_f, stream_t]),

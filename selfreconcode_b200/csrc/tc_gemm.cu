@@ -832,9 +832,50 @@ __global__ void embed_kernel(const __grid_constant__ EmbedArgs a) {
   }
 }
 
+// Backward of embed_kernel w.r.t. the points: gx [P*ch][ld] cotangent rows -> gp [P][3].  Value row: d PE / d p; tangent
+// rows (ch = 4): the tangent entries themselves depend on p (second derivative of the encoding).  One thread per point.
+__global__ void embed_bwd_kernel(const float* __restrict__ pts, long long P, int multires, const float* __restrict__ gx,
+                                 int ld, int ch, float* __restrict__ gp, float pw0, float pw1, float pw2, float pw3,
+                                 float pw4, float pw5, float pw6, float pw7) {
+  const float pw[8] = {pw0, pw1, pw2, pw3, pw4, pw5, pw6, pw7};
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const float* gv = gx + (size_t)p * ch * ld;
+    float out[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float x = pts[p * 3 + j];
+      float acc = gv[j];
+      const float* gt = ch == 4 ? gv + (size_t)(1 + j) * ld : nullptr;   // tangent row d/dp_j: only column j is non-zero
+      float freq = 1.0f;
+      for (int b = 0; b < multires; ++b, freq *= 2.0f) {
+        float sn, cs;
+        sincosf(x * freq, &sn, &cs);
+        const float w = pw[b] * freq;
+        const int ks = 3 + 6 * b + j, kc = ks + 3;
+        acc += w * (cs * gv[ks] - sn * gv[kc]);
+        if (gt) acc -= w * freq * (sn * gt[ks] + cs * gt[kc]);
+      }
+      out[j] = acc;
+    }
+    gp[p * 3] = out[0]; gp[p * 3 + 1] = out[1]; gp[p * 3 + 2] = out[2];
+  }
+}
+
 }  // namespace sr_tc
 
 extern "C" {
+
+int sr_tc_embed_backward(const float* pts, int64_t P, int multires, const float* pe_w, int ch, const float* gx, int ld,
+                         float* gp, cudaStream_t s) {
+  if (!pts || !gx || !gp || !pe_w || P <= 0 || (ch != 1 && ch != 4) || multires < 0 || multires > 8 ||
+      ld < 3 + 6 * multires)
+    return SR_EINVAL;
+  float w[8];
+  for (int i = 0; i < 8; ++i) w[i] = i < multires ? pe_w[i] : 0.f;
+  sr_tc::embed_bwd_kernel<<<sr_grid_for(P, 256, 8), 256, 0, s>>>(pts, P, multires, gx, ld, ch, gp, w[0], w[1], w[2], w[3],
+                                                                  w[4], w[5], w[6], w[7]);
+  return sr_launch_status();
+}
 
 int sr_tc_embed(const float* pts, int64_t P, int multires, const float* pe_w, int ch,
                 const float* conds, const int64_t* batch_inds, int64_t pts_per_frame, int condlen,

@@ -119,6 +119,32 @@ class ImplicitNetwork(nn.Module):
         return sdf.view(-1, 1), grad, feat
 
     # ---- fused training path (tensor-core engine, forward tangents) --------------------------
+    def shared_weights(self):
+        """Context manager: evaluations inside it share ONE set of effective (weight-normed) weight tensors, i.e. one
+        weight-norm sub-graph for several forward_train calls that are back-propagated together."""
+        net = self
+
+        class _Ctx:
+            def __enter__(self):
+                net._weff = {}
+
+            def __exit__(self, *a):
+                net._weff = None
+
+        return _Ctx()
+
+    def _effective(self, l):
+        from selfreconcode_b200 import train_ops as T
+        lin = getattr(self, "lin" + str(l))
+        if not self.weight_norm:
+            return lin.weight
+        cache = getattr(self, "_weff", None)
+        if cache is None:
+            return T.weight_norm_eff(lin.weight_v, lin.weight_g)
+        if l not in cache:
+            cache[l] = T.weight_norm_eff(lin.weight_v, lin.weight_g)
+        return cache[l]
+
     def _train_ok(self):
         from selfreconcode_b200 import train_ops
         return train_ops.TC_TRAIN_ENABLED and self.multires > 0 and self.d_out == 1
@@ -138,7 +164,7 @@ class ImplicitNetwork(nn.Module):
         Ws, bs, acts, skips = [], [], [], []
         for l in range(L):
             lin = getattr(self, "lin" + str(l))
-            W = T.weight_norm_eff(lin.weight_v, lin.weight_g) if self.weight_norm else lin.weight
+            W = self._effective(l)
             b = lin.bias
             if l == L - 1 and not want_feat:      # value only: the feature head is not evaluated
                 W, b = W[:self.d_out], b[:self.d_out]

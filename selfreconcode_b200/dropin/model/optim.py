@@ -251,6 +251,8 @@ class OptimNetwork(nn.Module):
         stands for the template vertices the reference adds to the eikonal sample set (:543)."""
         device = frame_ids.device
         conf = self.conf
+        if getattr(self.sdf, "_weff", None) is not None:
+            self.sdf._weff = None        # a previous call that raised must not leave its weight sub-graph behind
         gtCs = datas['img'].to(device)
         N = gtCs.shape[0]
         cameras, H, W = self._cameras(N, device)
@@ -271,6 +273,9 @@ class OptimNetwork(nn.Module):
         nonmnfld_pnts.requires_grad_()
         fused_train = utils.train_fused(self.deformer, self.sdf) and self.netRender._train_ok() \
             if hasattr(self.netRender, "_train_ok") else False
+        import contextlib
+        shared = self.sdf.shared_weights() if fused_train else contextlib.nullcontext()
+        shared.__enter__()       # eikonal and surface-point evaluations share one weight-norm sub-graph
         if fused_train:
             # eikonal term on the tensor-core training engine: grad f is a forward-mode output (network.py:545-547)
             _, grad, _ = self.sdf.forward_train(nonmnfld_pnts, ratio, want_grad=True, want_feat=False)
@@ -282,6 +287,7 @@ class OptimNetwork(nn.Module):
         total_loss = total_loss + grad_loss * conf.get_float('grad_weight')
         total_loss = total_loss + self._regularisers(nonmnfld_pnts, base, N, d_cond, poses, trans, ratio, frame_ids)
         self.info['color_loss'] = -1.0
+        self._tmp_geom = None
         if self.info['rayInfo'][1] > 0:
             self.TmpPs = initTmpPs[check]
             self.TmpPs.requires_grad = True
@@ -292,10 +298,13 @@ class OptimNetwork(nn.Module):
             grad_d_p = None
             if fused_train:
                 # f, grad f, rendcond in one forward-mode sweep; D(p), dD/dp in another (network.py:606-610)
-                sdfs, nx, rendcond_p = self.sdf.forward_train(self.TmpPs, ratio, want_grad=True, want_feat=True)
+                sdfs, gf_raw, rendcond_p = self.sdf.forward_train(self.TmpPs, ratio, want_grad=True, want_feat=True)
                 self.sdf.rendcond = rendcond_p
-                nx = nx / nx.norm(dim=1, keepdim=True)
+                nx = gf_raw / gf_raw.norm(dim=1, keepdim=True)
                 defVs, grad_d_p = self.deformer.forward_train(self.TmpPs, defconds, self.batch_inds, ratio, True)
+                # grad f and dD/dp at the surface points, reused (detached) by the normal weights below and by
+                # propagateTmpPsGrad: the reference re-evaluates both there (network.py:625, 721-748)
+                self._tmp_geom = (self.TmpPs, gf_raw.detach(), grad_d_p.detach())
                 Jinv, inv_mask = utils.FastDiff3x3MinvFunction.apply(grad_d_p)
                 crays = utils.mv3(Jinv, self.rays.view(-1, 3))
                 crays = torch.where(inv_mask.view(-1, 1), crays, self.rays.detach())
@@ -316,8 +325,11 @@ class OptimNetwork(nn.Module):
                 total_loss = total_loss + conf.get_float('color_weight') * color_loss
             if 'normal' in datas and 'normal_weight' in conf and conf.get_float('normal_weight') > 0.:
                 if 'weighted_normal' in conf and conf.get_bool('weighted_normal'):
-                    cnx, _ = utils.compute_deformed_normals(self.sdf, self.deformer, self.TmpPs, defconds,
-                                                            self.batch_inds, ratio, 'test')
+                    if self._tmp_geom is not None:
+                        cnx = utils.deformed_normals_from(self._tmp_geom[1], self._tmp_geom[2])
+                    else:
+                        cnx, _ = utils.compute_deformed_normals(self.sdf, self.deformer, self.TmpPs, defconds,
+                                                                self.batch_inds, ratio, 'test')
                     weights = torch.clamp((-self.rays * cnx.detach()).sum(1).detach(), max=1., min=0.) ** 2
                 else:
                     weights = torch.ones(nx.shape[0], device=device)
@@ -337,6 +349,7 @@ class OptimNetwork(nn.Module):
                 normal_loss = _scatter_mean(normal_loss[valid], self.batch_inds[valid], N).mean()
                 self.info['normal_loss'] = normal_loss.item()
                 total_loss = total_loss + conf.get_float('normal_weight') * normal_loss
+        shared.__exit__(None, None, None)
         if count_step:
             self.forward_time += 1
         return total_loss
@@ -604,7 +617,10 @@ class OptimNetwork(nn.Module):
         p = self.TmpPs
         fusable = hasattr(self.sdf, "forward_fused") and hasattr(self.deformer, "forward_fused") \
             and self.deformer._fusable()
-        if fusable:
+        geom = getattr(self, "_tmp_geom", None)
+        if geom is not None and geom[0] is p:
+            grad_f_p, grad_d_p = geom[1], geom[2]        # evaluated at exactly these points by forward_rays
+        elif fusable:
             # grad f and dD/dp at p from the fused forward-mode kernels: no graph, no 1+3 VJP passes
             with torch.no_grad():
                 _, grad_f_p, _ = self.sdf.forward_fused(p.detach(), ratio, want_grad=True, want_feat=False)

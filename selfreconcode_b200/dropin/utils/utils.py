@@ -155,6 +155,16 @@ def compute_deformed_normals(sdf, deformer, ps, defconds, batch_inds, ratio, pha
     return nx, ds
 
 
+def deformed_normals_from(grad_f, J):
+    """normalize(J^-T grad f) (fallback J grad f where J is singular) from already evaluated grad f [P,3] and
+    dD/dp [P,3,3]: the no-graph core of compute_deformed_normals (utils/utils.py:139-152)."""
+    with torch.no_grad():
+        Jinv, ok = Fast3x3Minv(J.contiguous())
+        nx = mtv3(Jinv, grad_f)
+        nx = torch.where(ok.view(-1, 1), nx, mv3(J, grad_f))
+        return nx / nx.norm(dim=1, keepdim=True)
+
+
 def compute_cardinal_rays(deformer, ps, rays, defconds, batch_inds, ratio, phase):
     check = phase in ('train', 'Train')
     if not check and _fusable(deformer):

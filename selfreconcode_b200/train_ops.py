@@ -226,10 +226,59 @@ def tc_mlp(x0, cfg, weights, biases):
 # ------------------------------------------------------------------------------------------------
 # Embedding with forward tangents (model/Embedder.py:34-55 + utils/utils.py:40-46), differentiable torch ops
 # ------------------------------------------------------------------------------------------------
+class EmbedRowsFunction(torch.autograd.Function):
+    """embed_rows on two kernels (csrc/tc_gemm.cu: embed_kernel / embed_bwd_kernel) instead of ~40 torch launches
+    forward and ~80 backward: x0 rows incl. the latent-code columns; d/dp includes the second derivative of the
+    encoding that the tangent rows need; d/d(extra) is the slice of the value rows."""
+
+    @staticmethod
+    def forward(ctx, p, extra, multires, pe_w, ch, width):
+        lib = _lib.load()
+        pts = p.detach().contiguous().float()
+        P = pts.shape[0]
+        E = extra.shape[1] if extra is not None else 0
+        out = torch.empty((P * ch, width), dtype=torch.float32, device=pts.device)
+        pw = (C.c_float * 16)(*[float(pe_w[i]) if i < multires else 0.0 for i in range(16)])
+        ex = extra.detach().contiguous().float() if extra is not None else None
+        with torch.cuda.device(pts.device):
+            check(lib.sr_tc_embed(_p(pts), P, multires, pw, ch, _p(ex), None, 1 if ex is not None else 0, E, _p(out), width,
+                                  None, None, _stream()), "tc_embed")
+        ctx.save_for_backward(pts)
+        ctx.meta = (multires, [float(pe_w[i]) for i in range(multires)], ch, width, E)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gx):
+        (pts,) = ctx.saved_tensors
+        multires, pe_w, ch, width, E = ctx.meta
+        lib = _lib.load()
+        P = pts.shape[0]
+        gx = gx.contiguous().float()
+        gp = ge = None
+        if ctx.needs_input_grad[0]:
+            gp = torch.empty((P, 3), dtype=torch.float32, device=pts.device)
+            pw = (C.c_float * 16)(*[pe_w[i] if i < multires else 0.0 for i in range(16)])
+            with torch.cuda.device(pts.device):
+                check(lib.sr_tc_embed_backward(_p(pts), P, multires, pw, ch, _p(gx), width, _p(gp), _stream()),
+                      "tc_embed_backward")
+        if E and ctx.needs_input_grad[1]:
+            pe = 3 + 6 * multires
+            ge = gx.view(P, ch, width)[:, 0, pe:pe + E]
+        return gp, ge, None, None, None, None
+
+
+EMBED_KERNELS = True
+
+
 def embed_rows(p, multires, pe_w, ch, extra=None, ld=None):
     """p [P,3] -> x0 [P*ch, ld]: row 0 of a point = [p, w_k sin(2^k p), w_k cos(2^k p), ..., extra], rows 1..3 =
     d/dp_c of it (zero for `extra`, which does not depend on p).  `extra` [P,E] (latent code, view, ...)."""
     P = p.shape[0]
+    if EMBED_KERNELS and p.is_cuda and p.dtype == torch.float32 and multires <= 8:
+        E0 = extra.shape[1] if extra is not None else 0
+        width0 = ld if ld is not None else _pad(3 + 6 * multires + E0, 32)
+        return EmbedRowsFunction.apply(p, extra, multires, list(pe_w), ch, width0)
     freqs = [float(2 ** k) for k in range(multires)]
     vals = [p]
     for k, fr in enumerate(freqs):

@@ -154,3 +154,28 @@ def test_tc_mlp_function_vs_autograd(cuda_dev, name):
     assert errs["out"] < TOL[name][0], errs
     assert max(v for k, v in errs.items() if k != "out") < TOL[name][1], errs
     assert (x0g.grad[:, c["d_in"]:] == 0).all()
+
+
+def test_embed_kernels_match_torch_embedding(cuda_dev):
+    """EmbedRowsFunction (embed_kernel / embed_bwd_kernel) vs the differentiable torch restatement: rows, d/dp incl. the
+    second derivative that the tangent rows need, d/d(latent code)."""
+    from selfreconcode_b200 import train_ops as T
+    g = torch.Generator().manual_seed(1)
+    for ch, E in ((4, 128), (1, 0), (4, 0), (1, 128)):
+        p = (torch.rand(500, 3, generator=g) * 2 - 1).to(cuda_dev)
+        ex = torch.randn(500, E, generator=g).to(cuda_dev) if E else None
+        pe_w = [1.0, 1.0, 0.7, 0.2, 0.0, 0.0]
+        outs = {}
+        for mode in (True, False):
+            T.EMBED_KERNELS = mode
+            pp = p.clone().requires_grad_(True)
+            ee = ex.clone().requires_grad_(True) if E else None
+            x0 = T.embed_rows(pp, 6, pe_w, ch, extra=ee)
+            R = torch.randn(x0.shape, generator=torch.Generator().manual_seed(2)).to(cuda_dev)
+            (x0 * R).sum().backward()
+            outs[mode] = (x0.detach(), pp.grad, ee.grad if E else None)
+        T.EMBED_KERNELS = True
+        assert norm_err(outs[True][0].cpu().numpy(), outs[False][0].cpu().numpy()) < 2e-6
+        assert norm_err(outs[True][1].cpu().numpy(), outs[False][1].cpu().numpy()) < 1e-5
+        if E:
+            assert norm_err(outs[True][2].cpu().numpy(), outs[False][2].cpu().numpy()) < 1e-6
