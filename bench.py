@@ -322,7 +322,7 @@ def build_train(sc, dev, rank, world):
     cams = RectifiedPerspectiveCameras(f.detach(), pp.detach(), R, T.detach(), image_size=[(W, H)])
     # The seed of the real pipeline (rasterised deformed template, network.py:485-493) puts D(start) on the PIXEL's own
     # ray.  Setup-only stand-in: Gauss-Newton on {f(p) = 0, (D(p) - c) x v_pixel = 0} from the synthetic surface point,
-    # on top of the fused value / gradient / Jacobian kernels; rays that settle are kept, starts are jittered by 6e-5.
+    # on top of the fused value / gradient / Jacobian kernels; rays that settle are kept.
     bi_a, ri_a, ci_a = rays["batch_inds"][sel].to(dev), rays["rows"][sel].to(dev), rays["cols"][sel].to(dev)
     pix = torch.stack([ci_a, ri_a, torch.ones_like(ci_a)], dim=1).float()
     dc = [dcond.detach(), [poses.detach(), trans.detach()]]
@@ -347,7 +347,10 @@ def build_train(sc, dev, rank, world):
         ok = (fv.abs() < 2e-5) & (ang < 0.3 * synth.ang_threshold(sc["cam"], 0.5))
     keep = torch.nonzero(ok).view(-1)[:TRAIN_RAYS]
     assert keep.numel() > 0.6 * TRAIN_RAYS, "seed solve settled on %d of %d rays" % (keep.numel(), TRAIN_RAYS)
-    jit = 6e-5 * torch.randn(keep.numel(), 3, generator=g).to(dev)
+    # half of the seeds sit on the solution (converge at the first test: they carry the colour / normal / implicit-
+    # differentiation load), half are jittered by 2e-4 and exercise the tracer's iterations
+    jit = 2e-4 * torch.randn(keep.numel(), 3, generator=g).to(dev)
+    jit[::2] = 0.0
     seeds = dict(bi=bi_a[keep], ri=ri_a[keep], ci=ci_a[keep], init=p[keep] + jit)
     holder = types.SimpleNamespace(rasterizer=types.SimpleNamespace(cameras=cams))
     conf = synth.reference_config().get_config("loss_coarse")
