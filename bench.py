@@ -358,7 +358,9 @@ def build_train(sc, dev, rank, world):
     net.dataset = data
     params = [q for q in list(sdf.parameters()) + list(comp.parameters()) + list(rn.parameters()) +
               list(data.parameters()) if q.requires_grad]
-    opt = torch.optim.Adam(params, lr=1e-5)
+    # lr = 0: Adam runs in full (and bumps every parameter's version, so the engines re-fold / re-pack each step as in
+    # real training) but the synthetic seeds stay on the surface they were solved for
+    opt = torch.optim.Adam(params, lr=0.0)
     ar = parallel.GradAllReduce(params, timed=True)
     img = (torch.rand(TRAIN_FRAMES, H, W, 3, generator=g) * 2 - 1).to(dev)
     nrm = torch.nn.functional.normalize(torch.randn(TRAIN_FRAMES, H, W, 3, generator=g), dim=-1).to(dev)

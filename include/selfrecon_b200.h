@@ -368,6 +368,11 @@ int sr_band_select(const float* values, int64_t n, float center, float eps, int3
                    int32_t* counter, cudaStream_t s);
 int sr_sdf_forward_indexed(const sr_mlp_desc* net, const float* pts, int64_t P, const int32_t* index,
                            const int32_t* m_dev, float* sdf, cudaStream_t s);
+/* Same contract for the first `cap` entries of the list, as one column-split launch per layer (fp32 FMAs): ~0.1 ms for
+ * a short list where the persistent engine's per-tile latency is ~1 ms.  work = sr_sdf_small_work_bytes(cap) bytes. */
+int64_t sr_sdf_small_work_bytes(int cap);
+int sr_sdf_forward_small(const sr_mlp_desc* net, const float* pts, int64_t P, const int32_t* index,
+                         const int32_t* m_dev, float* sdf, void* work, int cap, cudaStream_t s);
 
 /* Pointwise stages of the tensor-core tracer (one OptimizeSurfacePs iteration =
  * embed -> sr_tc_linear x layers (forward, activations kept per layer) -> sr_tc_trace_mid -> sr_tc_linear x

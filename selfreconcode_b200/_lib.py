@@ -124,6 +124,8 @@ SIGNATURES = {
     "sr_svals3x3_f32": (C.c_int, [c_f, c_f, c_f, i64, stream_t]),
     "sr_svals3x3_bwd_f32": (C.c_int, [c_f, c_f, c_f, c_f, c_f, i64, stream_t]),
     "sr_band_select": (C.c_int, [c_f, i64, f32, f32, c_f, c_f, stream_t]),
+    "sr_sdf_small_work_bytes": (i64, [i32]),
+    "sr_sdf_forward_small": (C.c_int, [C.POINTER(MlpDesc), c_f, i64, c_f, c_f, c_f, c_f, i32, stream_t]),
     "sr_sdf_forward_indexed": (C.c_int, [C.POINTER(MlpDesc), c_f, i64, c_f, c_f, c_f, stream_t]),
     "sr_tc_shade_point": (C.c_int, [i64, c_f, c_f, c_f, c_f, i32, c_f, C.POINTER(LbsParams), c_f, c_f, c_f,
                                     c_f, stream_t]),

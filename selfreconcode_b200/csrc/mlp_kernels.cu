@@ -866,6 +866,98 @@ int validate_net(const sr_mlp_desc* net, int T) {
   return SR_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small-batch fp32 evaluation of the SDF value for a LIST of points (sign / threshold decisions on the few values the
+// tensor-core engine leaves inside its error band).  The persistent engine above is throughput-shaped: one CTA walks
+// all layers of a 64-row tile, ~1 ms of latency however few points there are.  Here every layer is one launch whose
+// CTAs split the COLUMNS (64 per CTA) and a group of 8 listed points, so a handful of points uses the whole GPU:
+// 9 launches of ~10-20 us.  Plain fp32 FMAs in k order; activations fp32 in global scratch [cap][512] x 2.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSmallPts = 8;     // listed points per CTA
+constexpr int kSmallCols = 64;   // output columns per CTA
+
+__global__ void __launch_bounds__(256)
+small_embed_kernel(const float* __restrict__ pts, const int32_t* __restrict__ index, const int32_t* __restrict__ m_dev,
+                   int cap, int multires, sr_mlp_desc net, float* __restrict__ emb, int ld) {
+  const int count = min(*m_dev, cap);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int gp = index[i];
+  float* e = emb + (size_t)i * ld;
+  float freq = 1.0f;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) e[j] = pts[(size_t)gp * 3 + j];
+  for (int b = 0; b < multires; ++b, freq *= 2.0f) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float sn, cs;
+      sincosf(pts[(size_t)gp * 3 + j] * freq, &sn, &cs);
+      e[3 + 6 * b + j] = net.pe_w[b] * sn;
+      e[6 + 6 * b + j] = net.pe_w[b] * cs;
+    }
+  }
+}
+
+struct SmallLayerArgs {
+  const float* wt;      // [kpad][npad] k-major folded weights
+  const float* bias;
+  int k, n, npad, act;
+  const float* in;      // [cap][ld_in] (previous activations or the embedding)
+  int ld_in, k_in;      // columns taken from `in`
+  const float* emb;     // skip source [cap][ld_emb] (or null): input = cat(in[:k_in], emb[:k - k_in]) * scale
+  int ld_emb;
+  float scale;
+  float* out;           // [cap][ld_out] (or null on the last layer)
+  int ld_out;
+  float* sdf;           // last layer: sdf[index[i]] = output column 0
+  const int32_t* index;
+  const int32_t* m_dev;
+  int cap;
+};
+
+__global__ void __launch_bounds__(256) small_layer_kernel(const __grid_constant__ SmallLayerArgs a) {
+  const int count = min(*a.m_dev, a.cap);
+  const int p0 = blockIdx.y * kSmallPts;
+  if (p0 >= count) return;
+  __shared__ float xs[kSmallPts][512];
+  const int np = min(kSmallPts, count - p0);
+  for (int idx = threadIdx.x; idx < kSmallPts * a.k; idx += blockDim.x) {
+    const int p = idx / a.k, k = idx % a.k;
+    float v = 0.f;
+    if (p < np) {
+      const size_t row = (size_t)(p0 + p);
+      v = k < a.k_in ? a.in[row * a.ld_in + k] : a.emb[row * a.ld_emb + (k - a.k_in)];
+      v *= a.scale;
+    }
+    xs[p][k] = v;
+  }
+  __syncthreads();
+  const int col = blockIdx.x * kSmallCols + (threadIdx.x & (kSmallCols - 1));
+  const int pg = threadIdx.x / kSmallCols;            // 4 point pairs
+  if (col >= a.n) return;
+  float acc0 = 0.f, acc1 = 0.f;
+  const float* w = a.wt + col;
+  const float* x0 = xs[2 * pg];
+  const float* x1 = xs[2 * pg + 1];
+  for (int k = 0; k < a.k; ++k) {
+    const float wv = __ldg(w + (size_t)k * a.npad);
+    acc0 = fmaf(x0[k], wv, acc0);
+    acc1 = fmaf(x1[k], wv, acc1);
+  }
+  const float b = a.bias[col];
+  float z[2] = {acc0 + b, acc1 + b};
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int p = 2 * pg + t;
+    if (p >= np) continue;
+    float v = z[t];
+    if (a.act == SR_ACT_SOFTPLUS100) { float d; v = softplus100(v, d); }
+    else if (a.act == SR_ACT_RELU) v = fmaxf(v, 0.f);
+    if (a.out) a.out[(size_t)(p0 + p) * a.ld_out + col] = v;
+    if (a.sdf && col == 0) a.sdf[a.index[p0 + p]] = v;
+  }
+}
+
 // ids of the values within eps of `center` -> list (warp-aggregated append; order is irrelevant
 // to the caller, which writes results back by id)
 __global__ void __launch_bounds__(256)
@@ -953,6 +1045,41 @@ int sr_sdf_forward_indexed(const sr_mlp_desc* net, const float* pts, int64_t P, 
   if ((rc = set_smem(sdf_kernel<0>))) return rc;
   const long long nt = (P + 63) / 64;
   sdf_kernel<0><<<grid_for_tiles(nt), kThreads, kDynSmem, s>>>(a);
+  return sr_launch_status();
+}
+
+int64_t sr_sdf_small_work_bytes(int cap) { return (int64_t)cap * (2 * 512 + 64) * 4; }
+
+// Value-only fp32 evaluation of the listed points with column-split launches (low latency for short lists); the
+// first `cap` entries of the list are handled here, the rest (if the list is longer) by the persistent engine.
+int sr_sdf_forward_small(const sr_mlp_desc* net, const float* pts, int64_t P, const int32_t* index, const int32_t* m_dev,
+                         float* sdf, void* work, int cap, cudaStream_t s) {
+  int rc = validate_net(net, 0);
+  if (rc) return rc;
+  if (P <= 0 || P > 0x7fffffffLL || !pts || !sdf || !index || !m_dev || !work || cap <= 0) return SR_EINVAL;
+  if (net->d_in != 3 + 6 * net->multires || net->d_in > 64) return SR_EINVAL;
+  float* emb = (float*)work;
+  float* bufs[2] = {emb + (size_t)cap * 64, emb + (size_t)cap * (64 + 512)};
+  small_embed_kernel<<<(cap + 255) / 256, 256, 0, s>>>(pts, index, m_dev, cap, net->multires, *net, emb, 64);
+  const float* in = emb;
+  int ld_in = 64, k_prev = net->d_in;
+  for (int l = 0; l < net->n_layers; ++l) {
+    const sr_mlp_layer& ly = net->layer[l];
+    if (ly.k > 512 || ly.n > 512) return SR_EUNSUPPORTED;
+    SmallLayerArgs a;
+    a.wt = ly.wt; a.bias = ly.bias; a.k = ly.k; a.n = ly.n; a.npad = ly.npad; a.act = ly.act;
+    a.in = in; a.ld_in = ld_in;
+    a.k_in = ly.skip ? ly.k - net->d_in : ly.k;
+    a.emb = ly.skip ? emb : nullptr; a.ld_emb = 64;
+    a.scale = ly.skip ? 0.70710678118654752440f : 1.0f;
+    const bool last = l == net->n_layers - 1;
+    a.out = last ? nullptr : bufs[l & 1]; a.ld_out = 512;
+    a.sdf = last ? sdf : nullptr; a.index = index; a.m_dev = m_dev; a.cap = cap;
+    (void)k_prev;
+    dim3 grid((ly.n + kSmallCols - 1) / kSmallCols, (cap + kSmallPts - 1) / kSmallPts);
+    small_layer_kernel<<<grid, 256, 0, s>>>(a);
+    in = bufs[l & 1]; ld_in = 512; k_prev = ly.n;
+  }
   return sr_launch_status();
 }
 

@@ -267,7 +267,7 @@ class LBSkinner(nn.Module):
         """Device-side state for the fused path (channels-last volume, rebuilt if `ws` changes)."""
         require_cuda(self.ws, "LBSkinner")
         sig = (self.ws.data_ptr(), self.ws._version, self.b_min.data_ptr(), self.b_min._version,
-               self.Js.data_ptr(), self.Js._version,
+               self.b_max.data_ptr(), self.b_max._version, self.Js.data_ptr(), self.Js._version,
                None if self.init_pose is None else (self.init_pose.data_ptr(), self.init_pose._version))
         if self._lbs is None or sig != self._lbs_sig:
             self._lbs = ops.LbsState(self.ws, self.b_min, self.b_max, self.Js,

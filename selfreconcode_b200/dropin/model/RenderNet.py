@@ -63,7 +63,7 @@ class RenderingNetwork_view_norm(nn.Module):
 
     def _train_ok(self):
         from selfreconcode_b200 import train_ops
-        return train_ops.TC_TRAIN_ENABLED and self.mode == 'idr' and self.multires_n == 0 and self.multires_v > 0
+        return train_ops.TC_TRAIN_ENABLED and self._fusable()
 
     def forward_train(self, points, normals, view_dirs, feature_vectors, ratio):
         """Differentiable colours on the tensor-core training engine (inputs and parameters)."""
@@ -83,11 +83,17 @@ class RenderingNetwork_view_norm(nn.Module):
         out = T.tc_mlp(x0, T.MlpConfig(acts, [False] * L, x.shape[1], 1, packs), Ws, bs)
         return torch.tanh(out)
 
+    def _fusable(self):
+        """Configurations the fused engines implement (config.conf's defaults): mode 'idr', PE on the view direction
+        only, layers at most 512 wide.  Anything else runs the torch ops below (same math, any configuration)."""
+        wide = max(getattr(self, "lin" + str(l)).bias.shape[0] for l in range(self.num_layers - 1))
+        return self.mode == 'idr' and self.multires_n == 0 and self.multires_v > 0 and wide <= 512
+
     def forward(self, points, normals, view_dirs, feature_vectors, ratio):
         require_cuda(points, "RenderingNetwork_view_norm.forward")
         if self._train_ok() and needs_autograd(points, normals, view_dirs, feature_vectors, *self.parameters()):
             return self.forward_train(points, normals, view_dirs, feature_vectors, ratio)
-        if not needs_autograd(points, normals, view_dirs, feature_vectors, *self.parameters()):
+        if self._fusable() and not needs_autograd(points, normals, view_dirs, feature_vectors, *self.parameters()):
             return ops.render_forward(self.fused(ratio), points, normals, view_dirs, feature_vectors)
         ratio = ratio_value(ratio, 'renderRatio')
 

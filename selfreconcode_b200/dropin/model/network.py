@@ -147,7 +147,7 @@ class ImplicitNetwork(nn.Module):
 
     def _train_ok(self):
         from selfreconcode_b200 import train_ops
-        return train_ops.TC_TRAIN_ENABLED and self.multires > 0 and self.d_out == 1
+        return train_ops.TC_TRAIN_ENABLED and self._fusable()
 
     def forward_train(self, input, ratio, want_grad=True, want_feat=True):
         """Differentiable (w.r.t. the input AND the parameters) evaluation on the tensor-core engine:
@@ -182,10 +182,16 @@ class ImplicitNetwork(nn.Module):
         return sdf, grad, feat
 
     # ---- reference surface ---------------------------------------------------------------
+    def _fusable(self):
+        """The fused engines implement d_out == 1 with a positional encoding and layers at most 512 wide (the
+        reference's getTmpSdf); other configurations (network.py:80,100) run the torch ops of _forward_autograd."""
+        wide = max(getattr(self, "lin" + str(l)).bias.shape[0] for l in range(self.num_layers - 1))
+        return self.multires > 0 and self.d_out == 1 and wide <= 512
+
     def forward(self, input, ratio):
         require_cuda(input, "ImplicitNetwork.forward")
         params_need = any(p.requires_grad for p in self.parameters())
-        if not needs_autograd(input) and not (torch.is_grad_enabled() and params_need):
+        if self._fusable() and not needs_autograd(input) and not (torch.is_grad_enabled() and params_need):
             sdf, _, feat = self.forward_fused(input, ratio, False, True)
             self.rendcond = feat
             return sdf

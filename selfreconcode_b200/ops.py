@@ -452,6 +452,9 @@ def sdf_forward(net, pts, want_grad=False, nfeat=0):
 
 
 _band_scratch = {}
+SMALL_REFINE = _os.environ.get("SELFRECON_B200_SMALL_REFINE", "1") != "0"
+SMALL_CAP = 4096
+_KERNELS_PER_CALL["sdf_forward_small"] = 10
 
 
 def sdf_refine_band(net, pts, sdf, center=0.0, eps=None):
@@ -473,8 +476,27 @@ def sdf_refine_band(net, pts, sdf, center=0.0, eps=None):
         cnt, lst = buf[0:1], buf[1:]
         cnt.zero_()
         check(lib.sr_band_select(_p(sdf), P, float(center), eps, _p(lst), _p(cnt), _stream()), "band_select")
-        check(lib.sr_sdf_forward_indexed(C.byref(net.desc), _p(pts), P, _p(lst), _p(cnt), _p(sdf), _stream()),
-              "sdf_forward_indexed")
+        if SMALL_REFINE:
+            # short lists: one column-split launch per layer (~0.1 ms) instead of the persistent engine (~1 ms per tile);
+            # the list is longer than SMALL_CAP only in degenerate cases -- then the persistent engine takes all of it
+            wkey = key + ("small",)
+            work = _band_scratch.get(wkey)
+            if work is None:
+                work = torch.empty((lib.sr_sdf_small_work_bytes(SMALL_CAP),), dtype=torch.uint8, device=dev)
+                _band_scratch[wkey] = work
+            check(lib.sr_sdf_forward_small(C.byref(net.desc), _p(pts), P, _p(lst), _p(cnt), _p(sdf), _p(work),
+                                           SMALL_CAP, _stream()), "sdf_forward_small")
+            over = _band_scratch.get(key + ("over",))
+            if over is None:
+                over = torch.empty((1,), dtype=torch.int32, device=dev)
+                _band_scratch[key + ("over",)] = over
+            torch.clamp(cnt - SMALL_CAP, min=0, out=over)
+            if P > SMALL_CAP:
+                check(lib.sr_sdf_forward_indexed(C.byref(net.desc), _p(pts), P, _p(lst[SMALL_CAP:]), _p(over), _p(sdf),
+                                                 _stream()), "sdf_forward_indexed")
+        else:
+            check(lib.sr_sdf_forward_indexed(C.byref(net.desc), _p(pts), P, _p(lst), _p(cnt), _p(sdf), _stream()),
+                  "sdf_forward_indexed")
     return sdf
 
 
