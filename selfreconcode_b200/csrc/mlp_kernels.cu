@@ -921,10 +921,11 @@ __global__ void __launch_bounds__(256) small_layer_kernel(const __grid_constant_
   if (p0 >= count) return;
   __shared__ float xs[kSmallPts][512];
   const int np = min(kSmallPts, count - p0);
-  for (int idx = threadIdx.x; idx < kSmallPts * a.k; idx += blockDim.x) {
-    const int p = idx / a.k, k = idx % a.k;
+  const int k8s = (a.k + 7) & ~7;
+  for (int idx = threadIdx.x; idx < kSmallPts * k8s; idx += blockDim.x) {
+    const int p = idx / k8s, k = idx % k8s;
     float v = 0.f;
-    if (p < np) {
+    if (p < np && k < a.k) {
       const size_t row = (size_t)(p0 + p);
       v = k < a.k_in ? a.in[row * a.ld_in + k] : a.emb[row * a.ld_emb + (k - a.k_in)];
       v *= a.scale;
@@ -939,10 +940,17 @@ __global__ void __launch_bounds__(256) small_layer_kernel(const __grid_constant_
   const float* w = a.wt + col;
   const float* x0 = xs[2 * pg];
   const float* x1 = xs[2 * pg + 1];
-  for (int k = 0; k < a.k; ++k) {
-    const float wv = __ldg(w + (size_t)k * a.npad);
-    acc0 = fmaf(x0[k], wv, acc0);
-    acc1 = fmaf(x1[k], wv, acc1);
+  // the folded weights are zero padded to kpad (a multiple of 8) rows: 8 loads in flight per step, FMAs in k order
+  const int k8 = (a.k + 7) & ~7;
+  for (int k = 0; k < k8; k += 8) {
+    float wv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + (size_t)(k + u) * a.npad);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      acc0 = fmaf(x0[k + u], wv[u], acc0);
+      acc1 = fmaf(x1[k + u], wv[u], acc1);
+    }
   }
   const float b = a.bias[col];
   float z[2] = {acc0 + b, acc1 + b};
