@@ -34,6 +34,7 @@ TC_REFINE = _os.environ.get("SELFRECON_B200_TC_REFINE", "1") != "0"
 # size) and cannot remove the dominant source of per-ray divergence (sign(f) in the update when |f| is below the
 # engine's error): off by default, kept for experiments.
 TC_REFINE_TRACE = _os.environ.get("SELFRECON_B200_TC_REFINE_TRACE", "0") != "0"
+TC_DUAL_STREAM = _os.environ.get("SELFRECON_B200_TC_DUAL_STREAM", "1") != "0"
 
 import itertools as _it
 _uid_counter = _it.count()
@@ -912,6 +913,10 @@ class _TcTraceBuffers:
             self.acts_d = [u8(lib.sr_tc_act_bytes(P, _pad(def_net.desc.layer[i + 1].k, 32)))
                            for i in range(def_net.desc.n_layers - 1)]
             self.gd = f32(P, 64)
+            # the translator's sweeps run on a second stream beside the SDF's (own staging buffers)
+            self.A_in_d = u8(lib.sr_tc_act_bytes(P, 256))
+            self.A_d = [u8(lib.sr_tc_act_bytes(P, 512)) for _ in range(2)]
+            self.gskip_d = f32(P, 64)
 
 
 
@@ -985,6 +990,7 @@ class _TcTraceCtx:
         self.lbsT = torch.empty((n_frames, 3), dtype=torch.float32, device=dev)
         self.lbs_params = LbsParams()
         # borderline rays of each iteration, re-tested on the fp32 engine (one list, one count per iteration)
+        self.side_stream = torch.cuda.Stream(device=dev)
         self.recheck = torch.empty((P,), dtype=torch.int32, device=dev)
         self.recheck_counts = torch.empty((times + 1,), dtype=torch.int32, device=dev)
         self.rev_scratch = _trace_scratch(dev)
@@ -1020,8 +1026,22 @@ def _tc_trace_body(lib, G, sdf_net, def_net, ts, td, tp, P, times, condlen, has_
         # ---- forward sweeps (each layer keeps its output tiles for the reverse sweep)
         check(lib.sr_tc_embed(_p(pts), P, ds.multires, pw_s, 1, None, None, 0, 0, _p(B.emb_s), B.ld_s,
                               _p(idx), _p(m_dev), _stream()), "tc_embed")
+        # The SDF sweep (9 launches) and the translator sweep (5 launches) of an iteration are independent: on two
+        # streams the second grid's CTAs move into the SMs the first grid's last wave leaves idle (5.3 waves of row
+        # tiles per launch at 50 333 rays) and into its ramp / tail, instead of waiting for the whole grid.
+        dual = TC_DUAL_STREAM and def_net is not None
+        if dual:
+            main = torch.cuda.current_stream()
+            side = G.side_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                check(lib.sr_tc_embed(_p(pts), P, dd.multires, pw_d, 1, _p(conds), _p(bi), 0, condlen,
+                                      _p(B.emb_d), B.ld_d, _p(idx), _p(m_dev), _stream()), "tc_embed")
+                _tc_forward_sweep(lib, def_net, td, B.emb_d, B.ld_d, B.A_in_d, B.acts_d, P, m_dev, B.off)
         _tc_forward_sweep(lib, sdf_net, ts, B.emb_s, B.ld_s, B.A_in, B.acts_s, P, m_dev, B.f)
-        if def_net is not None:
+        if dual:
+            main.wait_stream(side)
+        elif def_net is not None:
             check(lib.sr_tc_embed(_p(pts), P, dd.multires, pw_d, 1, _p(conds), _p(bi), 0, condlen,
                                   _p(B.emb_d), B.ld_d, _p(idx), _p(m_dev), _stream()), "tc_embed")
             _tc_forward_sweep(lib, def_net, td, B.emb_d, B.ld_d, B.A_in, B.acts_d, P, m_dev, B.off)
@@ -1042,8 +1062,15 @@ def _tc_trace_body(lib, G, sdf_net, def_net, ts, td, tp, P, times, condlen, has_
         if a_out is None:
             break
         # ---- reverse sweeps + update
+        if dual:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                _tc_backward_sweep(lib, def_net, td, B.cot_d, B.A_d, B.acts_d, P, m_dev, B.gd, B.gskip_d,
+                                   3 + 6 * dd.multires)
         _tc_backward_sweep(lib, sdf_net, ts, B.cot_s, B.A, B.acts_s, P, m_dev, B.gs, B.gskip, ds.d_in)
-        if def_net is not None:
+        if dual:
+            main.wait_stream(side)
+        elif def_net is not None:
             _tc_backward_sweep(lib, def_net, td, B.cot_d, B.A, B.acts_d, P, m_dev, B.gd, B.gskip,
                                3 + 6 * dd.multires)
         has_skip = any(l["skip"] for l in ts.layers)
@@ -1086,7 +1113,7 @@ def trace_surface_points_tc(sdf_net, def_net, lbs, cam_pos, rays, init_pts, batc
            lbs.ws_cl.data_ptr() if lbs is not None else 0, cp, float(dthreshold), float(athreshold),
            float(w1), float(w2), tuple(ds.pe_w[i] for i in range(ds.multires)),
            tuple(dd.pe_w[i] for i in range(dd.multires)) if dd is not None else (),
-           TC_REFINE_TRACE, TC_EPS_F, TC_EPS_A)
+           TC_REFINE_TRACE, TC_EPS_F, TC_EPS_A, TC_DUAL_STREAM)
     G = _tc_trace_ctx.get(key)
     if G is None:
         if len(_tc_trace_ctx) >= 4:
@@ -1160,6 +1187,17 @@ def _tc_layers_from_rows(lib, tcn, d_in, emb, ld, M, ch, n_out_last=None, skip_e
     return out
 
 
+_side_streams = {}
+
+
+def _side_stream(dev):
+    st = _side_streams.get(dev.index)
+    if st is None:
+        st = torch.cuda.Stream(device=dev)
+        _side_streams[dev.index] = st
+    return st
+
+
 def shade_and_render_tc(sdf_full, def_net, lbs, render_net, pts, rays, batch_inds, conds, nfeat=256):
     """Shading of the infer path on the tensor-core engine: SDF and translator sweeps with forward
     tangents (4 rows per point), pointwise geometry, then the rendering network.
@@ -1172,8 +1210,19 @@ def shade_and_render_tc(sdf_full, def_net, lbs, render_net, pts, rays, batch_ind
     bi = batch_inds.contiguous().to(torch.int64) if batch_inds is not None else None
     lib = _lib.load()
     with torch.cuda.device(dev):
-        s4 = tc_mlp_forward(sdf_full, pts, ch=4)                      # [4P, 1+nfeat]
-        o4 = tc_mlp_forward(def_net, pts, ch=4, conds=conds, batch_inds=bi) if def_net is not None else None
+        if TC_DUAL_STREAM and def_net is not None:
+            # SDF and translator sweeps are independent: second stream (see _tc_trace_body)
+            main = torch.cuda.current_stream()
+            side = _side_stream(dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                o4 = tc_mlp_forward(def_net, pts, ch=4, conds=conds, batch_inds=bi)
+            s4 = tc_mlp_forward(sdf_full, pts, ch=4)                  # [4P, 1+nfeat]
+            main.wait_stream(side)
+            o4.record_stream(main)
+        else:
+            s4 = tc_mlp_forward(sdf_full, pts, ch=4)
+            o4 = tc_mlp_forward(def_net, pts, ch=4, conds=conds, batch_inds=bi) if def_net is not None else None
         normals = torch.empty((P, 3), dtype=torch.float32, device=dev)
         crays = torch.empty((P, 3), dtype=torch.float32, device=dev)
         dpos = torch.empty((P, 3), dtype=torch.float32, device=dev)
