@@ -147,7 +147,7 @@ struct EpiRow {
 // zero padding / skip-connection columns of the next layer's input are produced).
 template <int ACT, int CH, bool MUL>
 __device__ __forceinline__ void epi_chunk(const LayerArgs& a, const EpiRow& r, uint32_t (&v)[32], int chunk,
-                                          bool live) {
+                                          bool live, bool wait_v = false) {
   const int c0 = r.nt * BN + chunk * 32;
   float o[32];
   if (live) {
@@ -160,11 +160,27 @@ __device__ __forceinline__ void epi_chunk(const LayerArgs& a, const EpiRow& r, u
       // optional fp32 act'(z) of the previous layer's VALUE rows (written by its forward launch as `dstash`)
       const float* stash = a.dstash == nullptr ? nullptr
                            : a.dstash + (size_t)(CH == 4 ? (r.row & ~3LL) : r.row) * r.ds_ld + c0;
+      const bool use_stash = (ACT == SR_ACT_SOFTPLUS100) && stash != nullptr && r.row_ok;
+      // all global operands of the chunk first (8 x 16 B of activation tiles, 8 x 16 B of stash): 16 loads in flight
+      // per thread -- with two epilogue warps per scheduler nothing else hides their latency
+      uint4 q0[4], q1[4];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const uint4 q0 = *reinterpret_cast<const uint4*>(mt + (size_t)g * (BM * 8));
-        const uint4 q1 = *reinterpret_cast<const uint4*>(mt + (size_t)g * (BM * 8) + A_PLANE);
-        const uint32_t w0[4] = {q0.x, q0.y, q0.z, q0.w}, w1[4] = {q1.x, q1.y, q1.z, q1.w};
+        q0[g] = __ldg(reinterpret_cast<const uint4*>(mt + (size_t)g * (BM * 8)));
+        q1[g] = __ldg(reinterpret_cast<const uint4*>(mt + (size_t)g * (BM * 8) + A_PLANE));
+      }
+      float st[32];
+      if (use_stash) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(stash) + j4);
+          st[4 * j4] = t.x; st[4 * j4 + 1] = t.y; st[4 * j4 + 2] = t.z; st[4 * j4 + 3] = t.w;
+        }
+      }
+      if (wait_v) tmem_wait(v);     // the accumulator chunk was requested by the caller before this function
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint32_t w0[4] = {q0[g].x, q0[g].y, q0[g].z, q0[g].w}, w1[4] = {q1[g].x, q1[g].y, q1[g].z, q1[g].w};
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int j = g * 8 + e;
@@ -177,7 +193,7 @@ __device__ __forceinline__ void epi_chunk(const LayerArgs& a, const EpiRow& r, u
             if constexpr (ACT == SR_ACT_SOFTPLUS100) {
               // training: act'(z) kept in fp32 by the forward sweep (recomputing it from the 16-bit-mantissa
               // activation tiles costs 100 x 2^-17 relative on 1 - act'); the tracer recomputes (no stash traffic)
-              d = (stash != nullptr && r.row_ok && c0 + j < a.n) ? stash[j] : 1.0f - fast_ex2(kk * as);
+              d = use_stash ? st[j] : 1.0f - fast_ex2(kk * as);
             } else if constexpr (ACT == SR_ACT_RELU) d = as > 0.f ? 1.f : 0.f;
             else d = 1.f;
             if (c0 + j < a.n) val = r.row_ok ? val * d : 0.f;
@@ -188,17 +204,20 @@ __device__ __forceinline__ void epi_chunk(const LayerArgs& a, const EpiRow& r, u
             //   tangent rows:  u_bar_c = act'(z) t_bar_c
             //   value row   :  z_bar   = act'(z) a_bar + act''(z) sum_c t_bar_c u_c
             // and act'' u_c = 100 (1 - act') t_c for softplus(beta = 100), 0 for ReLU -- no division by act'.
-            const float av = __shfl_sync(0xffffffffu, as, r.lane & ~3);   // the point's value-row activation
             float d;
             if constexpr (ACT == SR_ACT_SOFTPLUS100) {
-              d = (stash != nullptr && r.row_ok && c0 + j < a.n) ? stash[j] : 1.0f - fast_ex2(kk * av);
-            } else if constexpr (ACT == SR_ACT_RELU) d = av > 0.f ? 1.f : 0.f;
-            else d = 1.f;
+              if (use_stash) d = st[j];       // the four rows of a point read the value row's stash entry
+              else d = 1.0f - fast_ex2(kk * __shfl_sync(0xffffffffu, as, r.lane & ~3));
+            } else if constexpr (ACT == SR_ACT_RELU) {
+              d = __shfl_sync(0xffffffffu, as, r.lane & ~3) > 0.f ? 1.f : 0.f;
+            } else d = 1.f;
             float cross = 0.f;
             if constexpr (ACT == SR_ACT_SOFTPLUS100) {
-              const float prod = r.is_val ? 0.f : val * (as * a.mul_inv_scale);    // t_bar_c * t_c
-              cross = __shfl_down_sync(0xffffffffu, prod, 1) + __shfl_down_sync(0xffffffffu, prod, 2) +
-                      __shfl_down_sync(0xffffffffu, prod, 3);
+              // sum of t_bar_c * t_c over the three tangent lanes of the point (butterfly inside the lane quad)
+              float prod = r.is_val ? 0.f : val * (as * a.mul_inv_scale);
+              prod += __shfl_xor_sync(0xffffffffu, prod, 1);
+              prod += __shfl_xor_sync(0xffffffffu, prod, 2);
+              cross = prod;
             }
             if (c0 + j < a.n) {
               float o4 = val * d;
@@ -210,6 +229,7 @@ __device__ __forceinline__ void epi_chunk(const LayerArgs& a, const EpiRow& r, u
         }
       }
     } else {
+      if (wait_v) tmem_wait(v);
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) {
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + c0) + j4);
@@ -434,8 +454,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(const __grid_cons
       } else {
         for (int i = 0; i < 4; ++i) {
           uint32_t v[32];
-          if (i < n_live) { tmem_ld32_async(taddr0 + i * 32, v); tmem_wait(v); }
-          epi_chunk<ACT, CH, MUL>(a, r, v, half * 4 + i, i < n_live);
+          // the chunk's global operands are requested inside epi_chunk BEFORE it waits for the TMEM load
+          if (i < n_live) tmem_ld32_async(taddr0 + i * 32, v);
+          epi_chunk<ACT, CH, MUL>(a, r, v, half * 4 + i, i < n_live, i < n_live);
         }
       }
       tc_fence_before();
@@ -694,8 +715,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       } else {
         for (int i = 0; i < 4; ++i) {
           uint32_t v[32];
-          if (i < n_live) { tmem_ld32_async(taddr0 + i * 32, v); tmem_wait(v); }
-          epi_chunk<ACT, CH, MUL>(a, r, v, half * 4 + i, i < n_live);
+          // the chunk's global operands are requested inside epi_chunk BEFORE it waits for the TMEM load
+          if (i < n_live) tmem_ld32_async(taddr0 + i * 32, v);
+          epi_chunk<ACT, CH, MUL>(a, r, v, half * 4 + i, i < n_live, i < n_live);
         }
       }
       tc_fence_before();
