@@ -158,9 +158,11 @@ __device__ __forceinline__ void epi_chunk(const LayerArgs& a, const EpiRow& r, u
                                 (size_t)(r.row_in_tile >> 3) * 64 + (r.row_in_tile & 7) * 8;
       const float kk = -144.26950408889634f * a.mul_inv_scale;   // -100 log2(e) / scale
       // optional fp32 act'(z) of the previous layer's VALUE rows (written by its forward launch as `dstash`)
-      const float* stash = a.dstash == nullptr ? nullptr
-                           : a.dstash + (size_t)(CH == 4 ? (r.row & ~3LL) : r.row) * r.ds_ld + c0;
-      const bool use_stash = (ACT == SR_ACT_SOFTPLUS100) && stash != nullptr && r.row_ok;
+      // rows past M read row 0's entries (discarded below): the predicate stays warp-uniform, so the warp is
+      // converged at the .aligned TMEM wait that follows the loads
+      const long long srow = r.row_ok ? (CH == 4 ? (r.row & ~3LL) : r.row) : 0;
+      const float* stash = a.dstash == nullptr ? nullptr : a.dstash + (size_t)srow * r.ds_ld + c0;
+      const bool use_stash = (ACT == SR_ACT_SOFTPLUS100) && stash != nullptr;
       // all global operands of the chunk first (8 x 16 B of activation tiles, 8 x 16 B of stash): 16 loads in flight
       // per thread -- with two epilogue warps per scheduler nothing else hides their latency
       uint4 q0[4], q1[4];
@@ -177,6 +179,7 @@ __device__ __forceinline__ void epi_chunk(const LayerArgs& a, const EpiRow& r, u
           st[4 * j4] = t.x; st[4 * j4 + 1] = t.y; st[4 * j4 + 2] = t.z; st[4 * j4 + 3] = t.w;
         }
       }
+      __syncwarp();
       if (wait_v) tmem_wait(v);     // the accumulator chunk was requested by the caller before this function
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
