@@ -303,6 +303,28 @@ int sr_tc_linear(const void* A, const void* W, const float* bias, int64_t M, int
                  int out_col0, int out_n, float* dstash, const void* mul_tiles, int mul_K, int mul_act,
                  float mul_scale, const int32_t* m_dev, cudaStream_t s);
 
+/* One step of a whole-sweep launch: the arguments of sr_tc_linear for one layer (pointers first, then ints). */
+typedef struct sr_tc_step {
+  const void* A;          /* tiled input activations (width K) */
+  const void* W;          /* packed weights (sr_tc_pack_weights) */
+  const float* bias;      /* [pad256(N)] */
+  void* A_next;           /* tiled output (width K_next) or NULL */
+  const float* skip_src;  /* fp32 rows appended after column n_valid (skip connection) or NULL */
+  float* out;             /* fp32 row-major output or NULL */
+  const void* mul_tiles;  /* reverse step: the forward sweep's activation tiles of the previous layer, or NULL */
+  float* dstash;          /* fp32 act'(z) stash (training) or NULL */
+  int32_t N, K, n_valid, act, K_next, skip_n, skip_ld, out_ld, out_col0, out_n, mul_K, mul_act;
+  float scale, mul_scale;
+} sr_tc_step;
+
+/* sr_tc_sweep: L <= 12 chained steps (step l+1 reads the tiles step l wrote) in ONE launch: a CTA pair keeps its
+ * row tiles through all steps, the only inter-step dependency is inside a CTA (network.py:66-83 ImplicitNetwork.forward
+ * layer loop; its reverse for the tracer's gradient, FindSurfacePs.py:128-140).  Same results as L sr_tc_linear calls.
+ * Restrictions: activations NONE / SOFTPLUS100 / RELU; a buffer must not be used with two different tile widths
+ * (SR_EINVAL).  m_dev: optional device-side row count. */
+int sr_tc_sweep(const sr_tc_step* steps, int L, int64_t M, int ch, const int32_t* m_dev, cudaStream_t s);
+
+
 /* Mesh rasteriser for the ray seed (replaces pytorch3d.renderer.MeshRasterizer in model/network.py:492 / :345 with
  * faces_per_pixel = 1, blur_radius = 0, perspective_correct = True; consumer: utils/FindSurfacePs.py:5-29).
  * verts_screen [N,V,3] = (pixel x = column, pixel y = row, camera depth z); faces [F,3] int64; keys = scratch of

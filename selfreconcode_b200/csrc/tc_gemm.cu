@@ -737,6 +737,254 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   }
 }
 
+// ---- whole-sweep kernel: all layers of a forward or reverse sweep in ONE launch ---------------------------
+// A CTA pair keeps its row tiles through every layer of the sweep: pair p owns the row-pair tiles
+// {p, p + npairs, ...} (256 rows each) in EVERY step.  The activations a step's epilogue writes for rows R are
+// exactly what the same CTA loads as the next step's A operand for rows R, so the only dependency between steps
+// is inside a CTA: the producer waits until the eight epilogue warps have finished the previous step on that row
+// tile (per-warp progress counters in shared memory, release / acquire, with a generic->async proxy fence on both
+// sides because the tiles are written with st.global and read back by the bulk-copy engine).  No grid or cluster
+// barrier between layers, one TMEM allocation, one barrier set-up and one launch ramp per SWEEP instead of per
+// layer; the smem ring and the two TMEM accumulators simply keep rolling across the layer boundary, so the first
+// MMAs of step l+1 overlap the last epilogue of step l whenever a pair owns more than one row tile.
+// Narrow steps (N < 256: the SDF's last layer, the input gradient of the reverse sweep) run as one N = 256 tile on
+// zero-padded weight rows.  Buffers that hold tiles of different widths must be distinct: tile (mt, kc) sits at
+// (mt * KC + kc), so two layouts of one buffer alias ACROSS row tiles (the host wrapper checks this).
+constexpr int kMaxSteps = 12;
+struct StepArgs {
+  LayerArgs la;
+  int act;       // SR_ACT_* of a forward step / of the PREVIOUS layer for a reverse (mul) step
+  int mul;       // 1: reverse step (acc * act'(z_prev))
+};
+struct SweepArgs {
+  StepArgs step[kMaxSteps];
+  int L;
+  int last_plain;   // the last step is a plain linear step (no activation, no act' multiply): the network's output layer
+                    // in a forward sweep, the input gradient in a reverse sweep
+};
+
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void st_release_smem(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(sr_smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_smem(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(sr_smem_u32(p)) : "memory");
+  return v;
+}
+
+// one accumulator (this warp's 32 lanes x its 128-column half) -> epilogue
+template <int ACT, int CH, bool MUL, bool DB = true>
+__device__ __forceinline__ void epi_item(const LayerArgs& a, const EpiRow& r, uint32_t taddr0, int n_live, int half) {
+  if constexpr (CH == 1 && !MUL && DB) {
+    uint32_t va[32], vb[32];
+    if (n_live > 0) tmem_ld32_async(taddr0, va);
+#pragma unroll
+    for (int i = 0; i < 4; i += 2) {
+      if (i < n_live) tmem_wait(va);
+      if (i + 1 < n_live) tmem_ld32_async(taddr0 + (i + 1) * 32, vb);
+      epi_chunk<ACT, CH, MUL>(a, r, va, half * 4 + i, i < n_live);
+      if (i + 1 < n_live) tmem_wait(vb);
+      if (i + 2 < 4 && i + 2 < n_live) tmem_ld32_async(taddr0 + (i + 2) * 32, va);
+      epi_chunk<ACT, CH, MUL>(a, r, vb, half * 4 + i + 1, i + 1 < n_live);
+    }
+  } else {
+    for (int i = 0; i < 4; ++i) {
+      uint32_t v[32];
+      if (i < n_live) tmem_ld32_async(taddr0 + i * 32, v);
+      epi_chunk<ACT, CH, MUL>(a, r, v, half * 4 + i, i < n_live, i < n_live);
+    }
+  }
+}
+
+// <ACT, MUL>: activation / mode of every step but (optionally) the last -- the two epilogues a sweep needs
+template <int ACT, int CH, bool MUL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    tc_sweep_pair_kernel(const __grid_constant__ SweepArgs sw) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem);
+  __nv_bfloat16* sW = reinterpret_cast<__nv_bfloat16*>(smem + (size_t)P_STAGES * A_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)P_STAGES * (A_STAGE_BYTES + PB_STAGE_BYTES));
+  uint64_t* full = bars;                    // [P_STAGES]
+  uint64_t* pfull = bars + P_STAGES;        // [P_STAGES]  (used in the leader)
+  uint64_t* empty = bars + 2 * P_STAGES;    // [P_STAGES]
+  uint64_t* tfull = bars + 3 * P_STAGES;    // [2]
+  uint64_t* tempty = tfull + 2;             // [2]         (used in the leader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint32_t* done = tmem_slot + 2;           // [kEpiWarps] items finished by each epilogue warp of THIS CTA
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < P_STAGES; ++i) { sr_mbar_init(&full[i], 1); sr_mbar_init(&pfull[i], 1); sr_mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { sr_mbar_init(&tfull[i], 1); sr_mbar_init(&tempty[i], 2 * kEpiWarps); }
+    for (int i = 0; i < kEpiWarps; ++i) done[i] = 0u;
+    sr_fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     sr_smem_u32(tmem_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();         // `done` zeroed before any role reads it
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const LayerArgs& a0 = sw.step[0].la;
+  long long Mrows = a0.M;
+  int MTe = a0.MT;
+  if (a0.m_dev != nullptr) {
+    const long long md = (long long)(*a0.m_dev);
+    Mrows = md < a0.M ? md : a0.M;
+    MTe = (int)((Mrows + BM - 1) / BM);
+  }
+  const int nrp = (MTe + 1) / 2;                                   // row-pair tiles (256 rows)
+  const int pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int J = pair_id < nrp ? (nrp - pair_id + npairs - 1) / npairs : 0;   // row-pair tiles of this pair
+  const int L = sw.L;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      uint32_t items_before = 0;            // items of the steps before the previous one
+      for (int l = 0; l < L; ++l) {
+        const LayerArgs& a = sw.step[l].la;
+        const int NTp = l > 0 ? sw.step[l - 1].la.NT : 0;
+        for (int j = 0; j < J; ++j) {
+          const long long mt = (long long)(pair_id + j * npairs) * 2 + rank;
+          const bool have_a = mt < MTe;
+          for (int nt = 0; nt < a.NT; ++nt) {
+            for (int kc = 0; kc < a.KC; ++kc) {
+              mbar_wait_cluster(&empty[slot], phase ^ 1u);
+              sr_mbar_arrive_expect_tx(&full[slot], (have_a ? A_STAGE_BYTES : 0u) + PB_STAGE_BYTES);
+              sr_bulk_g2s(sW + (size_t)slot * PB_STAGE,
+                          a.Wp + (((size_t)nt * a.KC + kc) * 2 + rank) * PB_STAGE, PB_STAGE_BYTES, &full[slot]);
+              if (l > 0 && nt == 0 && kc == 0) {
+                // rows of tile j: every n-tile of the previous step must have left the epilogue (this CTA's warps)
+                const uint32_t need = items_before + (uint32_t)(j + 1) * (uint32_t)NTp;
+                for (int w = 0; w < kEpiWarps; ++w)
+                  while (ld_acquire_smem(&done[w]) < need) {}
+                fence_proxy_async();
+              }
+              if (have_a)
+                sr_bulk_g2s(sA + (size_t)slot * A_STAGE, a.A + a_tile_off(mt, kc, a.KC, 0), A_STAGE_BYTES, &full[slot]);
+              if (++slot == P_STAGES) { slot = 0; phase ^= 1u; }
+            }
+          }
+        }
+        if (l > 0) items_before += (uint32_t)J * (uint32_t)NTp;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      if (!leader) {
+        for (int l = 0; l < L; ++l) {
+          const LayerArgs& a = sw.step[l].la;
+          const int n_it = J * a.NT * a.KC;
+          for (int it = 0; it < n_it; ++it) {
+            sr_mbar_wait(&full[slot], phase);
+            mbar_arrive_remote(&pfull[slot], 0);
+            if (++slot == P_STAGES) { slot = 0; phase ^= 1u; }
+          }
+        }
+      } else {
+        int buf = 0;
+        uint32_t bphase = 0;
+        const int pa[3] = {0, 1, 0};
+        const int pw[3] = {1, 0, 0};
+        const uint32_t idesc = kIdescPair | ((uint32_t)(BN >> 3) << 17);
+        for (int l = 0; l < L; ++l) {
+          const LayerArgs& a = sw.step[l].la;
+          const int n_items = J * a.NT;
+          for (int item = 0; item < n_items; ++item) {
+            mbar_wait_cluster(&tempty[buf], bphase ^ 1u);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)buf * BN;
+            uint32_t accumulate = 0;
+            for (int kc = 0; kc < a.KC; ++kc) {
+              sr_mbar_wait(&full[slot], phase);
+              mbar_wait_cluster(&pfull[slot], phase);
+              tc_fence_after();
+              const uint32_t abase = sr_smem_u32(sA + (size_t)slot * A_STAGE);
+              const uint32_t wbase = sr_smem_u32(sW + (size_t)slot * PB_STAGE);
+#pragma unroll
+              for (int q = 0; q < 3; ++q) {
+#pragma unroll
+                for (int jj = 0; jj < BK / 16; ++jj) {
+                  const uint64_t ad = make_desc(abase + pa[q] * (A_PLANE * 2) + jj * 2 * (BM * 16), BM * 16, 128);
+                  const uint64_t bd = make_desc(wbase + pw[q] * (PB_PLANE * 2) + jj * 2 * (128 * 16), 128 * 16, 128);
+                  mma_bf16_pair(tmem_d, ad, bd, idesc, accumulate);
+                  accumulate = 1;
+                }
+              }
+              mma_commit_pair(&empty[slot]);
+              if (++slot == P_STAGES) { slot = 0; phase ^= 1u; }
+            }
+            mma_commit_pair(&tfull[buf]);
+            if (++buf == 2) { buf = 0; bphase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    EpiRow r;
+    r.row_in_tile = q * 32 + lane;
+    r.lane = lane;
+    r.is_val = (CH == 1) || ((lane & 3) == 0);
+    int buf = 0;
+    uint32_t bphase = 0;
+    uint32_t items = 0;
+    for (int l = 0; l < L; ++l) {
+      const LayerArgs& a = sw.step[l].la;
+      const bool plain = sw.last_plain && l == L - 1;
+      r.ds_ld = (size_t)a.NT * BN;
+      for (int j = 0; j < J; ++j) {
+        r.mt = (long long)(pair_id + j * npairs) * 2 + rank;
+        r.row = r.mt * BM + r.row_in_tile;
+        r.row_ok = r.row < Mrows;
+        const bool have_rows = r.mt < MTe;
+        for (int nt = 0; nt < a.NT; ++nt) {
+          r.nt = nt;
+          const int c_base = nt * BN + half * 128;
+          const int n_live = have_rows ? (a.n_gemm - c_base + 31) >> 5 : 0;
+          mbar_wait_cluster(&tfull[buf], bphase);
+          tc_fence_after();
+          const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * BN + half * 128;
+          if (have_rows) {
+            if (plain) epi_item<SR_ACT_NONE, CH, false, false>(a, r, taddr0, n_live, half);
+            else epi_item<ACT, CH, MUL>(a, r, taddr0, n_live, half);
+          }
+          tc_fence_before();
+          fence_proxy_async();          // this lane's tile stores -> visible to the bulk copies of the next step
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive_remote(&tempty[buf], 0);
+            st_release_smem(&done[warp - 2], ++items);
+          }
+          if (++buf == 2) { buf = 0; bphase ^= 1u; }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // ---- packing kernels -------------------------------------------------------------------------
 // fp32 row-major [M][K] (ld) -> tiled split-bf16 activations with KC = ceil(Kpad/32) chunks
 __global__ void pack_rows_kernel(const float* __restrict__ src, long long M, int K, int ld,
@@ -1031,6 +1279,80 @@ int sr_tc_linear(const void* A, const void* W, const float* bias, int64_t M, int
     const int grid = (int)(ntiles < SR_NUM_SMS_B200 ? ntiles : SR_NUM_SMS_B200);
     kern<<<grid, kThreads, kSmem, s>>>(a);
   }
+  return sr_launch_status();
+}
+int sr_tc_sweep(const sr_tc_step* steps, int L, int64_t M, int ch, const int32_t* m_dev, cudaStream_t s) {
+  using namespace sr_tc;
+  if (!steps || L <= 0 || L > kMaxSteps || M <= 0 || (ch != 1 && ch != 4)) return SR_EINVAL;
+  SweepArgs sw;
+  sw.L = L;
+  const int MT = (int)((M + BM - 1) / BM);
+  for (int l = 0; l < L; ++l) {
+    const sr_tc_step& t = steps[l];
+    if (!t.A || !t.W || !t.bias || t.N <= 0 || t.K <= 0 || (!t.A_next && !t.out)) return SR_EINVAL;
+    if (t.act != SR_ACT_NONE && t.act != SR_ACT_SOFTPLUS100 && t.act != SR_ACT_RELU) return SR_EINVAL;
+    if (t.mul_tiles && (t.mul_act != SR_ACT_NONE && t.mul_act != SR_ACT_SOFTPLUS100 && t.mul_act != SR_ACT_RELU))
+      return SR_EINVAL;
+    if (t.mul_tiles && t.mul_K < t.n_valid) return SR_EINVAL;
+    LayerArgs& a = sw.step[l].la;
+    a.A = (const __nv_bfloat16*)t.A; a.W = (const __nv_bfloat16*)t.W; a.bias = t.bias; a.M = M;
+    a.MT = MT; a.NT = (t.N + BN - 1) / BN; a.KC = (t.K + 31) / 32;
+    a.Wp = a.W + (size_t)a.NT * a.KC * W_STAGE;
+    a.n_gemm = t.N; a.n = t.n_valid; a.ch = ch;
+    a.A_next = (__nv_bfloat16*)t.A_next; a.KCn = t.A_next ? (t.K_next + 31) / 32 : 0;
+    a.scale = t.scale; a.skip_src = t.skip_src; a.skip_n = t.skip_n; a.skip_ld = t.skip_ld;
+    a.out = t.out; a.out_ld = t.out_ld; a.dstash = t.dstash; a.out_col0 = t.out_col0; a.out_n = t.out_n;
+    a.mul_tiles = (const __nv_bfloat16*)t.mul_tiles; a.mul_KC = (t.mul_K + 31) / 32;
+    a.mul_inv_scale = t.mul_scale != 0.f ? 1.0f / t.mul_scale : 1.0f; a.m_dev = m_dev;
+    sw.step[l].mul = t.mul_tiles ? 1 : 0;
+    sw.step[l].act = t.mul_tiles ? t.mul_act : t.act;
+  }
+  // one buffer, two tile widths: the layouts alias across row tiles, and pairs run through the steps unsynchronised
+  for (int i = 0; i < L; ++i)
+    for (int j = 0; j < L; ++j) {
+      const LayerArgs &x = sw.step[i].la, &y = sw.step[j].la;
+      if (x.A_next && x.A_next == y.A_next && x.KCn != y.KCn) return SR_EINVAL;
+      if (x.A_next && (const void*)x.A_next == (const void*)y.A && x.KCn != y.KC) return SR_EINVAL;
+      if (x.A == y.A && x.KC != y.KC) return SR_EINVAL;
+    }
+  // every step but an optional plain last one shares (activation, mode)
+  const int body_act = sw.step[0].act, body_mul = sw.step[0].mul;
+  const StepArgs& lastp = sw.step[L - 1];
+  sw.last_plain = (L > 1 || true) && !lastp.mul && lastp.act == SR_ACT_NONE && (body_mul || body_act != SR_ACT_NONE) ? 1 : 0;
+  for (int l = 0; l < L - (sw.last_plain ? 1 : 0); ++l)
+    if (sw.step[l].act != body_act || sw.step[l].mul != body_mul) return SR_EINVAL;
+  using Kern = void (*)(const SweepArgs);
+  Kern kern = nullptr;
+#define SR_SW(ACT_, CH_, MUL_) kern = (Kern)tc_sweep_pair_kernel<ACT_, CH_, MUL_>
+  const int key = (ch == 4 ? 8 : 0) + (body_mul ? 4 : 0) + body_act;
+  switch (key) {
+    case 0: SR_SW(SR_ACT_NONE, 1, false); break;
+    case 1: SR_SW(SR_ACT_SOFTPLUS100, 1, false); break;
+    case 2: SR_SW(SR_ACT_RELU, 1, false); break;
+    case 4: SR_SW(SR_ACT_NONE, 1, true); break;
+    case 5: SR_SW(SR_ACT_SOFTPLUS100, 1, true); break;
+    case 6: SR_SW(SR_ACT_RELU, 1, true); break;
+    case 8: SR_SW(SR_ACT_NONE, 4, false); break;
+    case 9: SR_SW(SR_ACT_SOFTPLUS100, 4, false); break;
+    case 10: SR_SW(SR_ACT_RELU, 4, false); break;
+    case 12: SR_SW(SR_ACT_NONE, 4, true); break;
+    case 13: SR_SW(SR_ACT_SOFTPLUS100, 4, true); break;
+    case 14: SR_SW(SR_ACT_RELU, 4, true); break;
+  }
+#undef SR_SW
+  if (!kern) return SR_EINVAL;
+  static bool attr_set_dev[64][16] = {};
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& attr_set = attr_set_dev[cur_dev & 63][key];
+  if (!attr_set) {
+    cudaError_t e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPair);
+    if (e1 != cudaSuccess) return (int)e1;
+    attr_set = true;
+  }
+  const int nrp = (MT + 1) / 2;
+  const int npairs = nrp < SR_NUM_SMS_B200 / 2 ? nrp : SR_NUM_SMS_B200 / 2;
+  kern<<<(unsigned)(2 * npairs), kThreads, kSmemPair, s>>>(sw);
   return sr_launch_status();
 }
 }

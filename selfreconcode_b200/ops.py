@@ -839,6 +839,53 @@ def tc_net(fused):
     return t
 
 
+TC_SWEEP = _os.environ.get("SELFRECON_B200_TC_SWEEP", "1") != "0"
+_SWEEP_ACTS = (0, 1, 2)      # SR_ACT_NONE / SOFTPLUS100 / RELU: what the whole-sweep kernel's epilogues cover
+_STEP_DEFAULTS = dict(A_next=None, K_next=0, scale=1.0, skip_src=None, skip_n=0, skip_ld=0, out=None, out_ld=0,
+                      out_col0=0, out_n=0, dstash=None, mul_tiles=None, mul_K=0, mul_act=0, mul_scale=1.0)
+
+
+def _tc_step(**kw):
+    """One layer launch of the tensor-core engine as a dict of sr_tc_linear's arguments (tensors, not pointers)."""
+    d = dict(_STEP_DEFAULTS)
+    d.update(kw)
+    return d
+
+
+def _run_steps(lib, steps, M, ch, m_dev):
+    """Chained layer launches (step l+1 reads the tiles step l wrote).  The longest leading run of steps that share
+    (activation, mode) -- plus a plain linear step ending it -- goes out as ONE whole-sweep launch (sr_tc_sweep: a CTA
+    pair keeps its row tiles through all layers); anything left runs one launch per layer."""
+    n = 0
+    if TC_SWEEP and len(steps) >= 2 and steps[0]["dstash"] is None:
+        kind = lambda t: (t["mul_act"] if t["mul_tiles"] is not None else t["act"], t["mul_tiles"] is not None)
+        body = kind(steps[0])
+        if body[0] in _SWEEP_ACTS:
+            while n < len(steps) and kind(steps[n]) == body and steps[n]["dstash"] is None:
+                n += 1
+            if n < len(steps) and kind(steps[n]) == (0, False) and steps[n]["dstash"] is None:
+                n += 1
+        if n < 2 or n > 12:
+            n = 0
+    if n:
+        arr = (_lib.TcStep * n)()
+        for t, c in zip(steps[:n], arr):
+            c.A, c.W, c.bias, c.A_next = _p(t["A"]), _p(t["W"]), _p(t["bias"]), _p(t["A_next"])
+            c.skip_src, c.out, c.mul_tiles, c.dstash = _p(t["skip_src"]), _p(t["out"]), _p(t["mul_tiles"]), None
+            c.N, c.K, c.n_valid, c.act, c.K_next = t["N"], t["K"], t["n_valid"], t["act"], t["K_next"]
+            c.skip_n, c.skip_ld, c.out_ld, c.out_col0, c.out_n = t["skip_n"], t["skip_ld"], t["out_ld"], \
+                t["out_col0"], t["out_n"]
+            c.mul_K, c.mul_act, c.scale, c.mul_scale = t["mul_K"], t["mul_act"], t["scale"], t["mul_scale"]
+        check(lib.sr_tc_sweep(arr, n, M, ch, _p(m_dev), _stream()), "tc_sweep")
+    for t in steps[n:]:
+        check(lib.sr_tc_linear(_p(t["A"]), _p(t["W"]), _p(t["bias"]), M, t["N"], t["K"], t["n_valid"], t["act"], ch,
+                               _p(t["A_next"]), t["K_next"], t["scale"], _p(t["skip_src"]), t["skip_n"],
+                               t["skip_ld"], _p(t["out"]), t["out_ld"], t["out_col0"], t["out_n"], _p(t["dstash"]),
+                               _p(t["mul_tiles"]), t["mul_K"], t["mul_act"], t["mul_scale"], _p(m_dev), _stream()),
+              "tc_linear")
+    return n
+
+
 def tc_mlp_forward(fused, pts, ch=1, conds=None, batch_inds=None, pts_per_frame=0, n_out=None,
                    want_dstash=False):
     """Whole MLP on the tensor-core engine: embed -> pack -> one tcgen05 launch per layer.
@@ -865,6 +912,7 @@ def tc_mlp_forward(fused, pts, ch=1, conds=None, batch_inds=None, pts_per_frame=
         K = ld
         out = None
         stashes = []
+        steps = []
         L = len(net.layers)
         for i, ly in enumerate(net.layers):
             last = i == L - 1
@@ -876,13 +924,14 @@ def tc_mlp_forward(fused, pts, ch=1, conds=None, batch_inds=None, pts_per_frame=
             o = torch.empty((M, nv), dtype=torch.float32, device=dev) if last else None
             ds = torch.empty((M, _pad(ly["n"], 256)), dtype=torch.float32, device=dev) \
                 if (want_dstash and not last) else None
-            check(lib.sr_tc_linear(_p(A), _p(ly["W"]), _p(ly["bias"]), M, ly["n"], K, nv, ly["act"], ch,
-                                   _p(A_next), Kn, 0.7071067811865476 if skip_next else 1.0,
-                                   _p(emb) if skip_next else None, d.d_in if skip_next else 0, ld, _p(o),
-                                   nv if last else 0, 0, nv, _p(ds), None, 0, 0, 1.0, None, _stream()), "tc_linear")
+            steps.append(_tc_step(A=A, W=ly["W"], bias=ly["bias"], N=ly["n"], K=K, n_valid=nv, act=ly["act"],
+                                  A_next=A_next, K_next=Kn, scale=0.7071067811865476 if skip_next else 1.0,
+                                  skip_src=emb if skip_next else None, skip_n=d.d_in if skip_next else 0, skip_ld=ld,
+                                  out=o, out_ld=nv if last else 0, out_n=nv, dstash=ds))
             if ds is not None:
                 stashes.append(ds)
             A, K, out = A_next, Kn, o
+        _run_steps(lib, steps, M, ch, None)
     return (out, stashes) if want_dstash else out
 
 
@@ -896,7 +945,12 @@ class _TcTraceBuffers:
         u8 = lambda n: torch.empty((n,), dtype=torch.uint8, device=dev)
         self.ld_s = _pad(sdf_net.desc.d_in, 32)
         self.emb_s = f32(P, self.ld_s)
-        self.A = [u8(lib.sr_tc_act_bytes(P, 512)) for _ in range(2)]
+        # reverse-sweep staging tiles: one pair per tile width (a buffer is never seen under two widths)
+        def rev_widths(net):
+            dd = net.desc
+            return {32} | {_pad(dd.layer[l - 1].n, 32) for l in range(1, dd.n_layers)}
+        ws = rev_widths(sdf_net) | (rev_widths(def_net) if def_net is not None else set())
+        self.A = {w: [u8(lib.sr_tc_act_bytes(P, w)) for _ in range(2)] for w in sorted(ws)}
         self.f = f32(P, 1)
         self.A_in = u8(lib.sr_tc_act_bytes(P, 256))
         self.acts_s = [u8(lib.sr_tc_act_bytes(P, _pad(sdf_net.desc.layer[i + 1].k, 32)))
@@ -915,7 +969,7 @@ class _TcTraceBuffers:
             self.gd = f32(P, 64)
             # the translator's sweeps run on a second stream beside the SDF's (own staging buffers)
             self.A_in_d = u8(lib.sr_tc_act_bytes(P, 256))
-            self.A_d = [u8(lib.sr_tc_act_bytes(P, 512)) for _ in range(2)]
+            self.A_d = {w: [u8(lib.sr_tc_act_bytes(P, w)) for _ in range(2)] for w in sorted(rev_widths(def_net))}
             self.gskip_d = f32(P, 64)
 
 
@@ -929,29 +983,45 @@ def _tc_forward_sweep(lib, net, tcn, emb, ld, A_in, acts, P, m_dev, out):
     K = ld
     cur = A_in
     L = len(tcn.layers)
+    steps = []
     for i, ly in enumerate(tcn.layers):
         last = i == L - 1
         nxt = tcn.layers[i + 1] if not last else None
         Kn = _pad(nxt["k"], 32) if nxt else 0
         skip_next = bool(nxt and nxt["skip"])
-        check(lib.sr_tc_linear(_p(cur), _p(ly["W"]), _p(ly["bias"]), P, ly["n"], K, ly["n"], ly["act"], 1,
-                               _p(acts[i]) if nxt else None, Kn,
-                               0.7071067811865476 if skip_next else 1.0, _p(emb) if skip_next else None,
-                               d.d_in if skip_next else 0, ld, _p(out) if last else None,
-                               out.shape[1] if last else 0, 0, ly["n"] if last else 0,
-                               None, None, 0, 0, 1.0, _p(m_dev), _stream()), "tc_linear")
+        steps.append(_tc_step(A=cur, W=ly["W"], bias=ly["bias"], N=ly["n"], K=K, n_valid=ly["n"], act=ly["act"],
+                              A_next=acts[i] if nxt else None, K_next=Kn,
+                              scale=0.7071067811865476 if skip_next else 1.0, skip_src=emb if skip_next else None,
+                              skip_n=d.d_in if skip_next else 0, skip_ld=ld, out=out if last else None,
+                              out_ld=out.shape[1] if last else 0, out_n=ly["n"] if last else 0))
         if nxt:
             cur, K = acts[i], Kn
+    _run_steps(lib, steps, P, 1, m_dev)
 
 
 def _tc_backward_sweep(lib, net, tcn, cot, A_bufs, acts, P, m_dev, g_out, g_skip, n_keep):
     """cotangent rows `cot` [P][32] of the net outputs -> d/d(embedded input) in g_out [P][ld]
-    (first n_keep columns), skip-connection part in g_skip.  acts = the forward sweep's tiles."""
+    (first n_keep columns), skip-connection part in g_skip.  acts = the forward sweep's tiles.
+    A_bufs: per tile width one pair of staging buffers ({width: [buf, buf]}; the whole-sweep kernel must not see one
+    buffer under two widths) or, legacy, a plain pair used for every width (per-layer launches only)."""
     d = net.desc
     L = len(tcn.layers)
-    check(lib.sr_tc_pack_rows(_p(cot), P, 32, 32, _p(A_bufs[0]), _p(m_dev), _stream()), "tc_pack_rows")
-    cur = 0
+    per_width = isinstance(A_bufs, dict)
+    flip = {}
+
+    def stage(width):
+        if not per_width:
+            i = flip.get(0, 0)
+            flip[0] = 1 - i
+            return A_bufs[i]
+        i = flip.get(width, 0)
+        flip[width] = 1 - i
+        return A_bufs[width][i]
+
+    cur = stage(32)
+    check(lib.sr_tc_pack_rows(_p(cot), P, 32, 32, _p(cur), _p(m_dev), _stream()), "tc_pack_rows")
     K = 32
+    steps = []
     for l in range(L - 1, -1, -1):
         ly = tcn.layers[l]
         n_prev = tcn.layers[l - 1]["n"] if l > 0 else 0
@@ -959,17 +1029,25 @@ def _tc_backward_sweep(lib, net, tcn, cot, A_bufs, acts, P, m_dev, g_out, g_skip
         if l > 0:
             Kn = _pad(n_prev, 32)
             want_skip = ly["skip"]
-            check(lib.sr_tc_linear(_p(A_bufs[cur]), _p(ly["Wb"]), _p(ly["zero_bias"]), P, ly["k"], K, n_prev, 0, 1,
-                                   _p(A_bufs[1 - cur]), Kn, scale, None, 0, 0,
-                                   _p(g_skip) if want_skip else None, g_skip.shape[1] if want_skip else 0,
-                                   n_prev, d.d_in if want_skip else 0, None, _p(acts[l - 1]),
-                                   _pad(ly["k"], 32), tcn.layers[l - 1]["act"], scale, _p(m_dev), _stream()),
-                  "tc_linear")
-            cur, K = 1 - cur, Kn
+            nxt = stage(Kn)
+            steps.append(_tc_step(A=cur, W=ly["Wb"], bias=ly["zero_bias"], N=ly["k"], K=K, n_valid=n_prev, act=0,
+                                  A_next=nxt, K_next=Kn, scale=scale, out=g_skip if want_skip else None,
+                                  out_ld=g_skip.shape[1] if want_skip else 0, out_col0=n_prev,
+                                  out_n=d.d_in if want_skip else 0, mul_tiles=acts[l - 1], mul_K=_pad(ly["k"], 32),
+                                  mul_act=tcn.layers[l - 1]["act"], mul_scale=scale))
+            cur, K = nxt, Kn
         else:
-            check(lib.sr_tc_linear(_p(A_bufs[cur]), _p(ly["Wb"]), _p(ly["zero_bias"]), P, ly["k"], K, ly["k"], 0, 1,
-                                   None, 0, scale, None, 0, 0, _p(g_out), g_out.shape[1], 0, n_keep, None,
-                                   None, 0, 0, 1.0, _p(m_dev), _stream()), "tc_linear")
+            steps.append(_tc_step(A=cur, W=ly["Wb"], bias=ly["zero_bias"], N=ly["k"], K=K, n_valid=ly["k"], act=0,
+                                  scale=scale, out=g_out, out_ld=g_out.shape[1], out_col0=0, out_n=n_keep))
+    if not per_width:
+        saved = globals()["TC_SWEEP"]
+        globals()["TC_SWEEP"] = False
+        try:
+            _run_steps(lib, steps, P, 1, m_dev)
+        finally:
+            globals()["TC_SWEEP"] = saved
+    else:
+        _run_steps(lib, steps, P, 1, m_dev)
 
 
 class _TcTraceCtx:
@@ -1113,7 +1191,7 @@ def trace_surface_points_tc(sdf_net, def_net, lbs, cam_pos, rays, init_pts, batc
            lbs.ws_cl.data_ptr() if lbs is not None else 0, cp, float(dthreshold), float(athreshold),
            float(w1), float(w2), tuple(ds.pe_w[i] for i in range(ds.multires)),
            tuple(dd.pe_w[i] for i in range(dd.multires)) if dd is not None else (),
-           TC_REFINE_TRACE, TC_EPS_F, TC_EPS_A, TC_DUAL_STREAM)
+           TC_REFINE_TRACE, TC_EPS_F, TC_EPS_A, TC_DUAL_STREAM, TC_SWEEP)
     G = _tc_trace_ctx.get(key)
     if G is None:
         if len(_tc_trace_ctx) >= 4:
