@@ -751,6 +751,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 // zero-padded weight rows.  Buffers that hold tiles of different widths must be distinct: tile (mt, kc) sits at
 // (mt * KC + kc), so two layouts of one buffer alias ACROSS row tiles (the host wrapper checks this).
 constexpr int kMaxSteps = 12;
+static_assert(kPlanes == 2, "the whole-sweep kernel issues the 3-term (2-plane) product");
 struct StepArgs {
   LayerArgs la;
   int act;       // SR_ACT_* of a forward step / of the PREVIOUS layer for a reverse (mul) step
