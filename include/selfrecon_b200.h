@@ -323,6 +323,9 @@ typedef struct sr_tc_step {
  * Restrictions: activations NONE / SOFTPLUS100 / RELU; a buffer must not be used with two different tile widths
  * (SR_EINVAL).  m_dev: optional device-side row count. */
 int sr_tc_sweep(const sr_tc_step* steps, int L, int64_t M, int ch, const int32_t* m_dev, cudaStream_t s);
+/* tuning knock-outs of the whole-sweep kernel (measurement only; bit 0 drops the epilogue's proxy fence and makes the
+ * results undefined).  Returns the previous flags. */
+int sr_tc_debug_sweep_flags(int flags);
 
 
 /* Mesh rasteriser for the ray seed (replaces pytorch3d.renderer.MeshRasterizer in model/network.py:492 / :345 with

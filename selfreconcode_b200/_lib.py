@@ -116,6 +116,7 @@ SIGNATURES = {
     "sr_tc_linear": (C.c_int, [c_f, c_f, c_f, i64, i32, i32, i32, i32, i32, c_f, i32, f32, c_f, i32,
                                i32, c_f, i32, i32, i32, c_f, c_f, i32, i32, f32, c_f, stream_t]),
     "sr_tc_sweep": (C.c_int, [C.POINTER(TcStep), i32, i64, i32, c_f, stream_t]),
+    "sr_tc_debug_sweep_flags": (C.c_int, [i32]),
     "sr_tc_trace_mid": (C.c_int, [c_f, c_f, i64, c_f, c_f, c_f, c_f, c_f, C.POINTER(LbsParams),
                                   C.POINTER(TraceParams), i32, c_f, c_f, c_f, i32, c_f, c_f, c_f, f32, f32,
                                   stream_t]),

@@ -760,6 +760,7 @@ struct StepArgs {
 struct SweepArgs {
   StepArgs step[kMaxSteps];
   int L;
+  int dbg;          // tuning knock-outs (sr_tc_debug_sweep_flags): 1 = no proxy fence in the epilogue (WRONG results)
   int last_plain;   // the last step is a plain linear step (no activation, no act' multiply): the network's output layer
                     // in a forward sweep, the input gradient in a reverse sweep
 };
@@ -967,11 +968,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             else epi_item<ACT, CH, MUL>(a, r, taddr0, n_live, half);
           }
           tc_fence_before();
-          fence_proxy_async();          // this lane's tile stores -> visible to the bulk copies of the next step
+          // this lane's tile stores -> visible to the bulk copies of the next step (nothing reads the last step's)
+          // (one fence + one progress update per ROW TILE: the next step needs all n-tiles of the row tile anyway;
+          //  fence.proxy.async is MEMBAR.GPU + FENCE.VIEW.ASYNC, i.e. it waits for this lane's stores)
+          ++items;
+          const bool publish = nt == a.NT - 1 && l + 1 < L;
+          if (publish && !(sw.dbg & 1)) fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
             mbar_arrive_remote(&tempty[buf], 0);
-            st_release_smem(&done[warp - 2], ++items);
+            if (publish) st_release_smem(&done[warp - 2], items);
           }
           if (++buf == 2) { buf = 0; bphase ^= 1u; }
         }
@@ -1282,11 +1288,19 @@ int sr_tc_linear(const void* A, const void* W, const float* bias, int64_t M, int
   }
   return sr_launch_status();
 }
+static int g_sweep_dbg = 0;
+int sr_tc_debug_sweep_flags(int flags) {
+  const int old = g_sweep_dbg;
+  g_sweep_dbg = flags;
+  return old;
+}
+
 int sr_tc_sweep(const sr_tc_step* steps, int L, int64_t M, int ch, const int32_t* m_dev, cudaStream_t s) {
   using namespace sr_tc;
   if (!steps || L <= 0 || L > kMaxSteps || M <= 0 || (ch != 1 && ch != 4)) return SR_EINVAL;
   SweepArgs sw;
   sw.L = L;
+  sw.dbg = g_sweep_dbg;
   const int MT = (int)((M + BM - 1) / BM);
   for (int l = 0; l < L; ++l) {
     const sr_tc_step& t = steps[l];
