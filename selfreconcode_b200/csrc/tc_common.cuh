@@ -12,7 +12,15 @@ namespace sr_tc {
 #endif
 constexpr int kPlanes = SR_TC_PLANES;
 constexpr int BM = 128, BN = 256, BK = 32, STAGES = kPlanes == 2 ? 4 : 3;
-constexpr int kEpiWarps = 8;               // two per TMEM lane quarter, each takes half the columns
+#ifndef SR_TC_EPI_WARPS
+#define SR_TC_EPI_WARPS 8
+#endif
+constexpr int kEpiWarps = SR_TC_EPI_WARPS;  // 8 or 16: two / four per TMEM lane quarter, each takes a column part
+constexpr int kColParts = kEpiWarps / 4;    // column parts of a 256-column accumulator
+constexpr int kPartCols = 256 / kColParts;  // 128 or 64 columns per epilogue warp
+constexpr int kChunks = kPartCols / 32;     // 32-column chunks per warp
+constexpr bool kEpiDoubleBuffer = kEpiWarps == 8;   // two TMEM register buffers only fit the 168-register budget
+static_assert(kEpiWarps == 8 || kEpiWarps == 16, "epilogue warps: 8 or 16");
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int A_PLANE = BM * BK;          // elements
 constexpr int W_PLANE = BN * BK;

@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(const __grid_cons
       r.nt = (int)(t % a.NT);
       r.row = r.mt * BM + r.row_in_tile;
       r.row_ok = r.row < Mrows;
-      const int c_base = r.nt * BN + half * 128;
+      const int c_base = r.nt * BN + half * kPartCols;
 #ifdef SR_TC_DBG_NOEPI    // tuning knock-out: accumulators are drained without being read
       const int n_live = 0;
       if (t >= 0) r.row_ok = false;
@@ -440,26 +440,26 @@ __global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(const __grid_cons
 #endif
       sr_mbar_wait(&tfull[buf], bphase);
       tc_fence_after();
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * BN + half * 128;
-      if constexpr (CH == 1 && !MUL) {
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * BN + half * kPartCols;
+      if constexpr (CH == 1 && !MUL && kEpiDoubleBuffer) {
         // two register buffers: the TMEM load of chunk i+1 is in flight while chunk i is processed
         uint32_t va[32], vb[32];
         if (n_live > 0) tmem_ld32_async(taddr0, va);
 #pragma unroll
-        for (int i = 0; i < 4; i += 2) {
+        for (int i = 0; i < kChunks; i += 2) {
           if (i < n_live) tmem_wait(va);
           if (i + 1 < n_live) tmem_ld32_async(taddr0 + (i + 1) * 32, vb);
-          epi_chunk<ACT, CH, MUL>(a, r, va, half * 4 + i, i < n_live);
+          epi_chunk<ACT, CH, MUL>(a, r, va, half * kChunks + i, i < n_live);
           if (i + 1 < n_live) tmem_wait(vb);
-          if (i + 2 < 4 && i + 2 < n_live) tmem_ld32_async(taddr0 + (i + 2) * 32, va);
-          epi_chunk<ACT, CH, MUL>(a, r, vb, half * 4 + i + 1, i + 1 < n_live);
+          if (i + 2 < kChunks && i + 2 < n_live) tmem_ld32_async(taddr0 + (i + 2) * 32, va);
+          epi_chunk<ACT, CH, MUL>(a, r, vb, half * kChunks + i + 1, i + 1 < n_live);
         }
       } else {
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < kChunks; ++i) {
           uint32_t v[32];
           // the chunk's global operands are requested inside epi_chunk BEFORE it waits for the TMEM load
           if (i < n_live) tmem_ld32_async(taddr0 + i * 32, v);
-          epi_chunk<ACT, CH, MUL>(a, r, v, half * 4 + i, i < n_live, i < n_live);
+          epi_chunk<ACT, CH, MUL>(a, r, v, half * kChunks + i, i < n_live, i < n_live);
         }
       }
       tc_fence_before();
@@ -696,31 +696,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 #else
       const bool have_rows = r.mt < MTe;
 #endif
-      const int c_base = r.nt * BN + half * 128;
+      const int c_base = r.nt * BN + half * kPartCols;
       const int n_live = have_rows ? (a.n_gemm - c_base + 31) >> 5 : 0;
       mbar_wait_cluster(&tfull[buf], bphase);
       tc_fence_after();
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * BN + half * 128;
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * BN + half * kPartCols;
       if (!have_rows) {
         // phantom row tile of an odd tile count: nothing to read or write
-      } else if constexpr (CH == 1 && !MUL) {
+      } else if constexpr (CH == 1 && !MUL && kEpiDoubleBuffer) {
         uint32_t va[32], vb[32];
         if (n_live > 0) tmem_ld32_async(taddr0, va);
 #pragma unroll
-        for (int i = 0; i < 4; i += 2) {
+        for (int i = 0; i < kChunks; i += 2) {
           if (i < n_live) tmem_wait(va);
           if (i + 1 < n_live) tmem_ld32_async(taddr0 + (i + 1) * 32, vb);
-          epi_chunk<ACT, CH, MUL>(a, r, va, half * 4 + i, i < n_live);
+          epi_chunk<ACT, CH, MUL>(a, r, va, half * kChunks + i, i < n_live);
           if (i + 1 < n_live) tmem_wait(vb);
-          if (i + 2 < 4 && i + 2 < n_live) tmem_ld32_async(taddr0 + (i + 2) * 32, va);
-          epi_chunk<ACT, CH, MUL>(a, r, vb, half * 4 + i + 1, i + 1 < n_live);
+          if (i + 2 < kChunks && i + 2 < n_live) tmem_ld32_async(taddr0 + (i + 2) * 32, va);
+          epi_chunk<ACT, CH, MUL>(a, r, vb, half * kChunks + i + 1, i + 1 < n_live);
         }
       } else {
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < kChunks; ++i) {
           uint32_t v[32];
           // the chunk's global operands are requested inside epi_chunk BEFORE it waits for the TMEM load
           if (i < n_live) tmem_ld32_async(taddr0 + i * 32, v);
-          epi_chunk<ACT, CH, MUL>(a, r, v, half * 4 + i, i < n_live, i < n_live);
+          epi_chunk<ACT, CH, MUL>(a, r, v, half * kChunks + i, i < n_live, i < n_live);
         }
       }
       tc_fence_before();
@@ -778,23 +778,23 @@ __device__ __forceinline__ uint32_t ld_acquire_smem(const uint32_t* p) {
 // one accumulator (this warp's 32 lanes x its 128-column half) -> epilogue
 template <int ACT, int CH, bool MUL, bool DB = true>
 __device__ __forceinline__ void epi_item(const LayerArgs& a, const EpiRow& r, uint32_t taddr0, int n_live, int half) {
-  if constexpr (CH == 1 && !MUL && DB) {
+  if constexpr (CH == 1 && !MUL && DB && kEpiDoubleBuffer) {
     uint32_t va[32], vb[32];
     if (n_live > 0) tmem_ld32_async(taddr0, va);
 #pragma unroll
-    for (int i = 0; i < 4; i += 2) {
+    for (int i = 0; i < kChunks; i += 2) {
       if (i < n_live) tmem_wait(va);
       if (i + 1 < n_live) tmem_ld32_async(taddr0 + (i + 1) * 32, vb);
-      epi_chunk<ACT, CH, MUL>(a, r, va, half * 4 + i, i < n_live);
+      epi_chunk<ACT, CH, MUL>(a, r, va, half * kChunks + i, i < n_live);
       if (i + 1 < n_live) tmem_wait(vb);
-      if (i + 2 < 4 && i + 2 < n_live) tmem_ld32_async(taddr0 + (i + 2) * 32, va);
-      epi_chunk<ACT, CH, MUL>(a, r, vb, half * 4 + i + 1, i + 1 < n_live);
+      if (i + 2 < kChunks && i + 2 < n_live) tmem_ld32_async(taddr0 + (i + 2) * 32, va);
+      epi_chunk<ACT, CH, MUL>(a, r, vb, half * kChunks + i + 1, i + 1 < n_live);
     }
   } else {
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kChunks; ++i) {
       uint32_t v[32];
       if (i < n_live) tmem_ld32_async(taddr0 + i * 32, v);
-      epi_chunk<ACT, CH, MUL>(a, r, v, half * 4 + i, i < n_live, i < n_live);
+      epi_chunk<ACT, CH, MUL>(a, r, v, half * kChunks + i, i < n_live, i < n_live);
     }
   }
 }
@@ -958,11 +958,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         const bool have_rows = r.mt < MTe;
         for (int nt = 0; nt < a.NT; ++nt) {
           r.nt = nt;
-          const int c_base = nt * BN + half * 128;
+          const int c_base = nt * BN + half * kPartCols;
           const int n_live = have_rows ? (a.n_gemm - c_base + 31) >> 5 : 0;
           mbar_wait_cluster(&tfull[buf], bphase);
           tc_fence_after();
-          const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * BN + half * 128;
+          const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * BN + half * kPartCols;
           if (have_rows) {
             if (plain) epi_item<SR_ACT_NONE, CH, false, false>(a, r, taddr0, n_live, half);
             else epi_item<ACT, CH, MUL>(a, r, taddr0, n_live, half);
