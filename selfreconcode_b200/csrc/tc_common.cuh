@@ -12,16 +12,23 @@ namespace sr_tc {
 #endif
 constexpr int kPlanes = SR_TC_PLANES;
 constexpr int BM = 128, BN = 256, BK = 32, STAGES = kPlanes == 2 ? 4 : 3;
-#ifndef SR_TC_EPI_WARPS
-#define SR_TC_EPI_WARPS 8
+// Epilogue warps per CTA, per kernel family: the forward epilogues (bias, activation, re-split) are latency-bound with
+// two warps per scheduler and fit 96 registers, so they run 16 warps (four per TMEM lane quarter, 64 columns each:
+// measured -7 % per layer at M = 50 333); the reverse epilogues prefetch their operand tiles and need the 168-register
+// budget of 8 warps (at 16 they spill: +40 %).
+#ifndef SR_TC_EPI_WARPS_FWD
+#define SR_TC_EPI_WARPS_FWD 16
 #endif
-constexpr int kEpiWarps = SR_TC_EPI_WARPS;  // 8 or 16: two / four per TMEM lane quarter, each takes a column part
-constexpr int kColParts = kEpiWarps / 4;    // column parts of a 256-column accumulator
-constexpr int kPartCols = 256 / kColParts;  // 128 or 64 columns per epilogue warp
-constexpr int kChunks = kPartCols / 32;     // 32-column chunks per warp
-constexpr bool kEpiDoubleBuffer = kEpiWarps == 8;   // two TMEM register buffers only fit the 168-register budget
-static_assert(kEpiWarps == 8 || kEpiWarps == 16, "epilogue warps: 8 or 16");
-constexpr int kThreads = 64 + 32 * kEpiWarps;
+#ifndef SR_TC_EPI_WARPS_REV
+#define SR_TC_EPI_WARPS_REV 8
+#endif
+__host__ __device__ constexpr int epi_warps(bool mul) { return mul ? SR_TC_EPI_WARPS_REV : SR_TC_EPI_WARPS_FWD; }
+__host__ __device__ constexpr int epi_threads(bool mul) { return 64 + 32 * epi_warps(mul); }
+__host__ __device__ constexpr int epi_part_cols(int ew) { return 256 / (ew / 4); }     // accumulator columns per epilogue warp
+__host__ __device__ constexpr int epi_chunks(int ew) { return epi_part_cols(ew) / 32; }  // 32-column chunks per warp
+static_assert((SR_TC_EPI_WARPS_FWD == 8 || SR_TC_EPI_WARPS_FWD == 16) &&
+              (SR_TC_EPI_WARPS_REV == 8 || SR_TC_EPI_WARPS_REV == 16), "epilogue warps: 8 or 16");
+constexpr int kMaxEpiWarps = 16;
 constexpr int A_PLANE = BM * BK;          // elements
 constexpr int W_PLANE = BN * BK;
 constexpr int A_STAGE = kPlanes * A_PLANE;   // 2 planes: 16 KB

@@ -307,7 +307,9 @@ __device__ __forceinline__ void epi_chunk(const LayerArgs& a, const EpiRow& r, u
 }
 
 template <int ACT, int CH, bool MUL>
-__global__ void __launch_bounds__(kThreads, 1) tc_layer_kernel(const __grid_constant__ LayerArgs a) {
+__global__ void __launch_bounds__(epi_threads(MUL), 1) tc_layer_kernel(const __grid_constant__ LayerArgs a) {
+  constexpr int kEpiWarps = epi_warps(MUL), kPartCols = epi_part_cols(kEpiWarps), kChunks = epi_chunks(kEpiWarps);
+  constexpr bool kEpiDoubleBuffer = kEpiWarps == 8;
   extern __shared__ __align__(1024) unsigned char smem[];
   __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem);
   __nv_bfloat16* sW = reinterpret_cast<__nv_bfloat16*>(smem + (size_t)STAGES * A_STAGE_BYTES);
@@ -548,8 +550,10 @@ __device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
 }
 
 template <int ACT, int CH, bool MUL>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(epi_threads(MUL), 1)
     tc_layer_pair_kernel(const __grid_constant__ LayerArgs a) {
+  constexpr int kEpiWarps = epi_warps(MUL), kPartCols = epi_part_cols(kEpiWarps), kChunks = epi_chunks(kEpiWarps);
+  constexpr bool kEpiDoubleBuffer = kEpiWarps == 8;
   extern __shared__ __align__(1024) unsigned char smem[];
   __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem);
   __nv_bfloat16* sW = reinterpret_cast<__nv_bfloat16*>(smem + (size_t)P_STAGES * A_STAGE_BYTES);
@@ -776,9 +780,10 @@ __device__ __forceinline__ uint32_t ld_acquire_smem(const uint32_t* p) {
 }
 
 // one accumulator (this warp's 32 lanes x its 128-column half) -> epilogue
-template <int ACT, int CH, bool MUL, bool DB = true>
+template <int ACT, int CH, bool MUL, int EW, bool DB = true>
 __device__ __forceinline__ void epi_item(const LayerArgs& a, const EpiRow& r, uint32_t taddr0, int n_live, int half) {
-  if constexpr (CH == 1 && !MUL && DB && kEpiDoubleBuffer) {
+  constexpr int kChunks = epi_chunks(EW);
+  if constexpr (CH == 1 && !MUL && DB && EW == 8) {
     uint32_t va[32], vb[32];
     if (n_live > 0) tmem_ld32_async(taddr0, va);
 #pragma unroll
@@ -801,8 +806,9 @@ __device__ __forceinline__ void epi_item(const LayerArgs& a, const EpiRow& r, ui
 
 // <ACT, MUL>: activation / mode of every step but (optionally) the last -- the two epilogues a sweep needs
 template <int ACT, int CH, bool MUL>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(epi_threads(MUL), 1)
     tc_sweep_pair_kernel(const __grid_constant__ SweepArgs sw) {
+  constexpr int kEpiWarps = epi_warps(MUL), kPartCols = epi_part_cols(kEpiWarps);
   extern __shared__ __align__(1024) unsigned char smem[];
   __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem);
   __nv_bfloat16* sW = reinterpret_cast<__nv_bfloat16*>(smem + (size_t)P_STAGES * A_STAGE_BYTES);
@@ -964,8 +970,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           tc_fence_after();
           const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * BN + half * kPartCols;
           if (have_rows) {
-            if (plain) epi_item<SR_ACT_NONE, CH, false, false>(a, r, taddr0, n_live, half);
-            else epi_item<ACT, CH, MUL>(a, r, taddr0, n_live, half);
+            if (plain) epi_item<SR_ACT_NONE, CH, false, kEpiWarps, false>(a, r, taddr0, n_live, half);
+            else epi_item<ACT, CH, MUL, kEpiWarps>(a, r, taddr0, n_live, half);
           }
           tc_fence_before();
           // this lane's tile stores -> visible to the bulk copies of the next step (nothing reads the last step's)
@@ -1280,11 +1286,11 @@ int sr_tc_linear(const void* A, const void* W, const float* bias, int64_t M, int
   if (pair) {
     const long long npt = (long long)((a.MT + 1) / 2) * a.NT;
     const long long npairs = npt < SR_NUM_SMS_B200 / 2 ? npt : SR_NUM_SMS_B200 / 2;
-    kern<<<(unsigned)(2 * npairs), kThreads, kSmemPair, s>>>(a);
+    kern<<<(unsigned)(2 * npairs), epi_threads(mul_tiles != nullptr), kSmemPair, s>>>(a);
   } else {
     const long long ntiles = (long long)a.MT * a.NT;
     const int grid = (int)(ntiles < SR_NUM_SMS_B200 ? ntiles : SR_NUM_SMS_B200);
-    kern<<<grid, kThreads, kSmem, s>>>(a);
+    kern<<<grid, epi_threads(mul_tiles != nullptr), kSmem, s>>>(a);
   }
   return sr_launch_status();
 }
@@ -1367,7 +1373,7 @@ int sr_tc_sweep(const sr_tc_step* steps, int L, int64_t M, int ch, const int32_t
   }
   const int nrp = (MT + 1) / 2;
   const int npairs = nrp < SR_NUM_SMS_B200 / 2 ? nrp : SR_NUM_SMS_B200 / 2;
-  kern<<<(unsigned)(2 * npairs), kThreads, kSmemPair, s>>>(sw);
+  kern<<<(unsigned)(2 * npairs), epi_threads(body_mul != 0), kSmemPair, s>>>(sw);
   return sr_launch_status();
 }
 }

@@ -839,7 +839,7 @@ def tc_net(fused):
     return t
 
 
-TC_SWEEP = _os.environ.get("SELFRECON_B200_TC_SWEEP", "1") != "0"
+TC_SWEEP = _os.environ.get("SELFRECON_B200_TC_SWEEP", "0") != "0"   # measured slower than per-layer launches
 _SWEEP_ACTS = (0, 1, 2)      # SR_ACT_NONE / SOFTPLUS100 / RELU: what the whole-sweep kernel's epilogues cover
 _STEP_DEFAULTS = dict(A_next=None, K_next=0, scale=1.0, skip_src=None, skip_n=0, skip_ld=0, out=None, out_ld=0,
                       out_col0=0, out_n=0, dstash=None, mul_tiles=None, mul_K=0, mul_act=0, mul_scale=1.0)

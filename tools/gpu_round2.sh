@@ -1,0 +1,14 @@
+mkdir -p gpurun_out
+timeout 600 python -X faulthandler -m pytest tests -m gpu -x -q -o faulthandler_timeout=150 > gpurun_out/pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest.log
+timeout 240 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" > gpurun_out/smoke.log 2>&1
+timeout 400 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2>&1
+timeout 100 python tools/sweep_bench.py 50333 > gpurun_out/sweep_bench3.log 2>&1
+grep -v "Warn\|WeightNorm" gpurun_out/smoke.log | tail -3; tail -4 gpurun_out/pytest.log; grep "M=" gpurun_out/sweep_bench3.log | grep -v "no epi"
+python - <<'PY'
+import json
+d=json.loads([l for l in open("gpurun_out/bench.log") if l.startswith("{")][-1])
+print("value", d["value"], "ray", d["ms_ray_part"], "mc", d["ms_mc_part"], "trace", d["roofline"]["trace"]["ms"], "e2e", d["e2e"]["value"], "frac", d["roofline"]["frac"], d["roofline"]["ms_per_launch"])
+t=d.get("train") or {}
+print("train", t.get("ms_per_step"), t.get("value"), t.get("ms_forward_incl_trace"), t.get("ms_backward"), t.get("ms_propagate"))
+print("parity", {k:v for k,v in d["parity"].items() if "mismatch" in k or "over_tol" in k or "identical" in k})
+PY
