@@ -145,7 +145,7 @@ struct EpiRow {
 // scaling (forward) or act' multiply (reverse), then the fp32 outputs, the act' stash and the
 // re-split bf16 tile of the next layer.  `live` = the chunk holds GEMM columns (else only the
 // zero padding / skip-connection columns of the next layer's input are produced).
-template <int ACT, int CH, bool MUL>
+template <int ACT, int CH, bool MUL, bool PF = true>
 __device__ __forceinline__ void epi_chunk(const LayerArgs& a, const EpiRow& r, uint32_t (&v)[32], int chunk,
                                           bool live, bool wait_v = false) {
   const int c0 = r.nt * BN + chunk * 32;
@@ -165,25 +165,42 @@ __device__ __forceinline__ void epi_chunk(const LayerArgs& a, const EpiRow& r, u
       const bool use_stash = (ACT == SR_ACT_SOFTPLUS100) && stash != nullptr;
       // all global operands of the chunk first (8 x 16 B of activation tiles, 8 x 16 B of stash): 16 loads in flight
       // per thread -- with two epilogue warps per scheduler nothing else hides their latency
-      uint4 q0[4], q1[4];
+      // (PF = false: the 16-warp build of the reverse kernels has 96 registers -- operands are requested per group of
+      //  8 columns and the extra warps hide the latency instead)
+      uint4 q0[PF ? 4 : 1], q1[PF ? 4 : 1];
+      float st[PF ? 32 : 1];
+      if constexpr (PF) {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        q0[g] = __ldg(reinterpret_cast<const uint4*>(mt + (size_t)g * (BM * 8)));
-        q1[g] = __ldg(reinterpret_cast<const uint4*>(mt + (size_t)g * (BM * 8) + A_PLANE));
-      }
-      float st[32];
-      if (use_stash) {
+        for (int g = 0; g < 4; ++g) {
+          q0[g] = __ldg(reinterpret_cast<const uint4*>(mt + (size_t)g * (BM * 8)));
+          q1[g] = __ldg(reinterpret_cast<const uint4*>(mt + (size_t)g * (BM * 8) + A_PLANE));
+        }
+        if (use_stash) {
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(stash) + j4);
-          st[4 * j4] = t.x; st[4 * j4 + 1] = t.y; st[4 * j4 + 2] = t.z; st[4 * j4 + 3] = t.w;
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(stash) + j4);
+            st[4 * j4] = t.x; st[4 * j4 + 1] = t.y; st[4 * j4 + 2] = t.z; st[4 * j4 + 3] = t.w;
+          }
         }
       }
       __syncwarp();
       if (wait_v) tmem_wait(v);     // the accumulator chunk was requested by the caller before this function
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const uint32_t w0[4] = {q0[g].x, q0[g].y, q0[g].z, q0[g].w}, w1[4] = {q1[g].x, q1[g].y, q1[g].z, q1[g].w};
+        uint4 a0, a1;
+        float sg[8];
+        if constexpr (PF) {
+          a0 = q0[g]; a1 = q1[g];
+        } else {
+          a0 = __ldg(reinterpret_cast<const uint4*>(mt + (size_t)g * (BM * 8)));
+          a1 = __ldg(reinterpret_cast<const uint4*>(mt + (size_t)g * (BM * 8) + A_PLANE));
+          if (use_stash) {
+            const float4 t0 = __ldg(reinterpret_cast<const float4*>(stash) + 2 * g);
+            const float4 t1 = __ldg(reinterpret_cast<const float4*>(stash) + 2 * g + 1);
+            sg[0] = t0.x; sg[1] = t0.y; sg[2] = t0.z; sg[3] = t0.w; sg[4] = t1.x; sg[5] = t1.y; sg[6] = t1.z; sg[7] = t1.w;
+          }
+        }
+        const uint32_t w0[4] = {a0.x, a0.y, a0.z, a0.w}, w1[4] = {a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int j = g * 8 + e;
@@ -196,7 +213,7 @@ __device__ __forceinline__ void epi_chunk(const LayerArgs& a, const EpiRow& r, u
             if constexpr (ACT == SR_ACT_SOFTPLUS100) {
               // training: act'(z) kept in fp32 by the forward sweep (recomputing it from the 16-bit-mantissa
               // activation tiles costs 100 x 2^-17 relative on 1 - act'); the tracer recomputes (no stash traffic)
-              d = use_stash ? st[j] : 1.0f - fast_ex2(kk * as);
+              d = use_stash ? (PF ? st[PF ? j : 0] : sg[e]) : 1.0f - fast_ex2(kk * as);
             } else if constexpr (ACT == SR_ACT_RELU) d = as > 0.f ? 1.f : 0.f;
             else d = 1.f;
             if (c0 + j < a.n) val = r.row_ok ? val * d : 0.f;
@@ -209,7 +226,7 @@ __device__ __forceinline__ void epi_chunk(const LayerArgs& a, const EpiRow& r, u
             // and act'' u_c = 100 (1 - act') t_c for softplus(beta = 100), 0 for ReLU -- no division by act'.
             float d;
             if constexpr (ACT == SR_ACT_SOFTPLUS100) {
-              if (use_stash) d = st[j];       // the four rows of a point read the value row's stash entry
+              if (use_stash) d = PF ? st[PF ? j : 0] : sg[e];   // the four rows of a point read the value row's stash entry
               else d = 1.0f - fast_ex2(kk * __shfl_sync(0xffffffffu, as, r.lane & ~3));
             } else if constexpr (ACT == SR_ACT_RELU) {
               d = __shfl_sync(0xffffffffu, as, r.lane & ~3) > 0.f ? 1.f : 0.f;
@@ -461,7 +478,7 @@ __global__ void __launch_bounds__(epi_threads(MUL), 1) tc_layer_kernel(const __g
           uint32_t v[32];
           // the chunk's global operands are requested inside epi_chunk BEFORE it waits for the TMEM load
           if (i < n_live) tmem_ld32_async(taddr0 + i * 32, v);
-          epi_chunk<ACT, CH, MUL>(a, r, v, half * kChunks + i, i < n_live, i < n_live);
+          epi_chunk<ACT, CH, MUL, kEpiWarps == 8>(a, r, v, half * kChunks + i, i < n_live, i < n_live);
         }
       }
       tc_fence_before();
@@ -724,7 +741,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(epi_threads(MUL), 1)
           uint32_t v[32];
           // the chunk's global operands are requested inside epi_chunk BEFORE it waits for the TMEM load
           if (i < n_live) tmem_ld32_async(taddr0 + i * 32, v);
-          epi_chunk<ACT, CH, MUL>(a, r, v, half * kChunks + i, i < n_live, i < n_live);
+          epi_chunk<ACT, CH, MUL, kEpiWarps == 8>(a, r, v, half * kChunks + i, i < n_live, i < n_live);
         }
       }
       tc_fence_before();
@@ -799,7 +816,7 @@ __device__ __forceinline__ void epi_item(const LayerArgs& a, const EpiRow& r, ui
     for (int i = 0; i < kChunks; ++i) {
       uint32_t v[32];
       if (i < n_live) tmem_ld32_async(taddr0 + i * 32, v);
-      epi_chunk<ACT, CH, MUL>(a, r, v, half * kChunks + i, i < n_live, i < n_live);
+      epi_chunk<ACT, CH, MUL, EW == 8>(a, r, v, half * kChunks + i, i < n_live, i < n_live);
     }
   }
 }
