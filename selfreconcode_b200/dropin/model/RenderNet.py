@@ -69,11 +69,9 @@ class RenderingNetwork_view_norm(nn.Module):
         """Differentiable colours on the tensor-core training engine (inputs and parameters)."""
         from selfreconcode_b200 import train_ops as T
         L = self.num_layers - 1
-        Ws, bs = [], []
-        for l in range(L):
-            lin = getattr(self, "lin" + str(l))
-            Ws.append(T.weight_norm_eff(lin.weight_v, lin.weight_g) if self.weight_norm else lin.weight)
-            bs.append(lin.bias)
+        lins = [getattr(self, "lin" + str(l)) for l in range(L)]
+        Ws = T.weight_norm_all(lins) if self.weight_norm else [lin.weight for lin in lins]
+        bs = [lin.bias for lin in lins]
         pe_w = ops.annealing_weights(self.multires_v, ratio_value(ratio, "renderRatio"))
         ev = T.embed_rows(view_dirs, self.multires_v, pe_w, 1, ld=3 + 6 * self.multires_v)
         x = torch.cat([points, ev, normals, feature_vectors], dim=-1)

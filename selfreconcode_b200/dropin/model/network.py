@@ -142,7 +142,10 @@ class ImplicitNetwork(nn.Module):
         if cache is None:
             return T.weight_norm_eff(lin.weight_v, lin.weight_g)
         if l not in cache:
-            cache[l] = T.weight_norm_eff(lin.weight_v, lin.weight_g)
+            # all layers in one launch (and one backward launch) the first time any of them is asked for
+            L = self.num_layers - 1
+            for i, W in enumerate(T.weight_norm_all([getattr(self, "lin" + str(i)) for i in range(L)])):
+                cache[i] = W
         return cache[l]
 
     def _train_ok(self):
@@ -162,9 +165,17 @@ class ImplicitNetwork(nn.Module):
         ch = 4 if want_grad else 1
         L = self.num_layers - 1
         Ws, bs, acts, skips = [], [], [], []
+        local = self.weight_norm and getattr(self, "_weff", None) is None
+        if local:
+            self._weff = {}          # this call's own weight-norm sub-graph (one fused launch)
+        try:
+            Weff = [self._effective(l) for l in range(L)]
+        finally:
+            if local:
+                self._weff = None
         for l in range(L):
             lin = getattr(self, "lin" + str(l))
-            W = self._effective(l)
+            W = Weff[l]
             b = lin.bias
             if l == L - 1 and not want_feat:      # value only: the feature head is not evaluated
                 W, b = W[:self.d_out], b[:self.d_out]
