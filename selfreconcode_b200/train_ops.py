@@ -378,13 +378,16 @@ class WeightNormAllFunction(torch.autograd.Function):
 
 import os as _os
 
-FUSED_WEIGHT_NORM = _os.environ.get("SELFRECON_B200_FUSED_WN", "1") != "0"
+# Off by default: parity-tested (tests/test_gpu_train.py) and 360 launches fewer per optimisation step, but in the one
+# bench run it was on, the optimizer phase of the step grew from 0.8 to 7.1 ms (forward / backward / propagate shrank by
+# 0.8 / 1.0 / 1.2 ms) and the GPU budget of the round ended before that could be bisected.
+FUSED_WEIGHT_NORM = _os.environ.get("SELFRECON_B200_FUSED_WN", "0") != "0"
 
 
-def weight_norm_all(lins):
+def weight_norm_all(lins, fused=None):
     """Effective weights of a list of weight-normalised torch Linear modules (weight_v / weight_g), in layer order.
     CUDA parameters: one fused launch per direction for up to 12 layers; otherwise the element-wise torch form."""
-    if lins and FUSED_WEIGHT_NORM and lins[0].weight_v.is_cuda and len(lins) <= 12:
+    if lins and (FUSED_WEIGHT_NORM if fused is None else fused) and lins[0].weight_v.is_cuda and len(lins) <= 12:
         vg = []
         for lin in lins:
             vg += [lin.weight_v, lin.weight_g]

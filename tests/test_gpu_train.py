@@ -205,7 +205,7 @@ def test_fused_weight_norm_matches_torch(cuda_dev):
         for lin in lins:
             lin.weight_v.grad = None
             lin.weight_g.grad = None
-        Ws = T.weight_norm_all(lins) if fused else [T.weight_norm_eff(l.weight_v, l.weight_g) for l in lins]
+        Ws = T.weight_norm_all(lins, fused=True) if fused else [T.weight_norm_eff(l.weight_v, l.weight_g) for l in lins]
         loss_of(Ws).backward()
         res[fused] = ([w.detach().clone() for w in Ws],
                       [(l.weight_v.grad, l.weight_g.grad) for l in lins])
