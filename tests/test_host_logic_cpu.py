@@ -77,3 +77,26 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.TcLayer) == 4 * 8 + 4 * 4
     assert _lib.TcStep.N.offset == 64 and _lib.TcStep.scale.offset == 112
     assert _lib.WnLayer.n.offset == 56
+
+
+def test_effective_weights_cache_and_fallback():
+    """ImplicitNetwork._effective / shared_weights (one weight-norm sub-graph per step) and train_ops.weight_norm_all
+    off the GPU: the element-wise torch form, same tensors inside one shared context, no state left behind."""
+    from helpers import dropin
+    dropin()
+    from selfreconcode_b200 import synth, train_ops as T
+    sdf = synth.make_sdf()
+    L = sdf.num_layers - 1
+    lins = [getattr(sdf, "lin%d" % l) for l in range(L)]
+    ref = [T.weight_norm_eff(lin.weight_v, lin.weight_g) for lin in lins]
+    assert all(torch.equal(a, b) for a, b in zip(T.weight_norm_all(lins), ref))
+    assert torch.equal(sdf._effective(3), ref[3])                 # no context: computed on demand
+    with sdf.shared_weights():
+        got = [sdf._effective(l) for l in range(L)]
+        assert all(torch.equal(a, b) for a, b in zip(got, ref))
+        assert sdf._effective(2) is got[2]                        # one sub-graph: the same tensor object
+    assert sdf._weff is None
+    # gradients flow to both parameters through the shared sub-graph
+    with sdf.shared_weights():
+        (sdf._effective(1).sum() + sdf._effective(1).pow(2).sum()).backward()
+    assert lins[1].weight_v.grad is not None and lins[1].weight_g.grad is not None
