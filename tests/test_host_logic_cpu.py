@@ -100,3 +100,19 @@ def test_effective_weights_cache_and_fallback():
     with sdf.shared_weights():
         (sdf._effective(1).sum() + sdf._effective(1).pow(2).sum()).backward()
     assert lins[1].weight_v.grad is not None and lins[1].weight_g.grad is not None
+
+
+def test_weight_norm_backward_formula():
+    """The closed form csrc/weight_norm.cu implements (gg = <gw, v>/||v||, gv = g/||v|| (gw - v <gw, v>/||v||^2))
+    against torch autograd of g v/||v|| in float64."""
+    g0 = torch.Generator().manual_seed(2)
+    v = torch.randn(7, 13, generator=g0, dtype=torch.float64, requires_grad=True)
+    g = torch.randn(7, 1, generator=g0, dtype=torch.float64, requires_grad=True)
+    gw = torch.randn(7, 13, generator=g0, dtype=torch.float64)
+    (g * v / v.norm(dim=1, keepdim=True) * gw).sum().backward()
+    nrm = v.detach().norm(dim=1, keepdim=True)
+    s = (gw * v.detach()).sum(1, keepdim=True)
+    gg = s / nrm
+    gv = g.detach() / nrm * (gw - v.detach() * s / nrm ** 2)
+    assert torch.allclose(gg, g.grad, rtol=1e-12, atol=1e-14)
+    assert torch.allclose(gv, v.grad, rtol=1e-12, atol=1e-14)
